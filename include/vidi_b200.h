@@ -1,0 +1,97 @@
+/* vidi_b200 -- C ABI of the B200 (sm_100a) kernel library behind the Vidi prefill path.
+ *
+ * The reference (bytedance/vidi) has no native code and no FFI: every GPU instruction on its hot path
+ * comes from PyTorch/cuBLAS/cuDNN, flash-attn 2 and liger-kernel calls made from Python.  Each entry
+ * point below therefore cites the *reference call site(s)* whose third-party kernels it replaces
+ * (paths relative to the reference repo root; K-numbers refer to SURVEY.md section 2.2).
+ *
+ * Conventions: plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; bf16
+ * tensors are row-major with an explicit leading dimension in ELEMENTS; `stream` is a cudaStream_t
+ * passed as void*; functions return 0 on success, non-zero on error (vidi_last_error() has the text);
+ * no function synchronises the stream.  No CPU fallback exists anywhere in this library.
+ */
+#ifndef VIDI_B200_H
+#define VIDI_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vidi_last_error(void);
+int vidi_abi_version(void);
+/* number of kernel launches issued through this library since the last reset (bench "gpu_launches") */
+int64_t vidi_launch_count(void);
+void vidi_reset_launch_count(void);
+
+/* activation / GLU codes for vidi_gemm_bf16 */
+#define VIDI_ACT_NONE 0
+#define VIDI_ACT_GELU_ERF 1   /* nn.GELU(): projector, pos-MLP, Whisper      (mm_layer/mlp.py:20, mm_vision/pos.py:38) */
+#define VIDI_ACT_GELU_TANH 2  /* gelu_pytorch_tanh: SigLIP MLP                (HF modeling_siglip.py SiglipMLP)       */
+#define VIDI_ACT_SOFTCAP 3    /* cap * tanh(x / cap): final logit soft-cap    (lmm/dattn/gemma.py:566-569)            */
+#define VIDI_ACT_SILU 4
+#define VIDI_GLU_NONE 0
+#define VIDI_GLU_GELU_TANH 1  /* Gemma2MLP  down(gelu_tanh(gate) * up)        (gemma.py:116-123 -> HF Gemma2MLP)      */
+#define VIDI_GLU_SILU 2       /* MistralMLP down(silu(gate) * up)             (Vidi_7B mistral.py:131-137)            */
+
+/* C[M,N] = epi(A[M,K] . W[N,K]^T): tcgen05/TMEM/TMA persistent GEMM.  Replaces every nn.Linear / conv-as-GEMM on the
+ * path: k_proj/v_proj (gemma.py:61-62), o_proj (gemma.py:94,197), Gemma2MLP (gemma.py:116-123), lm_head (gemma.py:565),
+ * SigLIP/Whisper linears (mm_vision/siglip.py:30, mm_audio/whisper.py:27), projector MLP (mm_layer/mlp.py:18-22),
+ * patch conv and Conv1d pools (multimodal.py:85-88,232).
+ *  bias: fp32 [N] or NULL.  residual: bf16 [M or res_mod, ldr] or NULL, added after the activation; if res_mod > 0 the
+ *  residual row is (row % res_mod) (position-embedding add).  glu != 0: W rows are packed per block_n tile as
+ *  [block_n/2 gate rows | block_n/2 up rows] and C has N/2 columns.  out_fp32: C is float.  block_n in {64,128,256}. */
+int vidi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                   const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                   int out_fp32, int glu, int block_n, void* stream);
+
+/* y = x_hat(x,eps) * (add_one ? 1+w : w) * out_scale.  Gemma2RMSNorm (gemma.py:107-111,162,184) / vidi RMSNorm (mm_layer/norm.py:17-25) */
+int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
+                 float out_scale, void* stream);
+/* x += post_mode ? G(y,w_post) : y ; h = norm(x, w_next) (h may be NULL).  gemma.py:198-202 and 116-123 fused */
+int vidi_residual_norm(void* x, int64_t ldx, const void* y, int64_t ldy, const void* w_post, const void* w_next, void* h,
+                       int64_t ldh, int rows, int D, float eps, int post_mode, int next_add_one, void* stream);
+/* nn.LayerNorm with fp32 affine (SigLIP / Whisper encoder layers) */
+int vidi_layernorm(const void* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
+                   float eps, void* stream);
+/* RMSNorm + up to 3 positional-table adds + token mask + llm norm + sqrt(D) scale in one pass
+ * (multimodal.py:193-206,241-250; gemma.py:353-356).  tabs: HOST array of ntab device pointers (fp32 [*,D]). */
+int vidi_mm_finish(const void* proj, int64_t ldp, const void* w_mod, const void* w_llm, const float* const* tabs,
+                   const int* divs, const int* mods, const int* offs, int ntab, int n_offset, int sample_valid,
+                   float normalizer, void* out, int64_t ldo, uint8_t* mask, int rows, int D, float eps, void* stream);
+/* weight-less rms_norm of fp32 rows (rms_norm(pos_mlp(.)), mm_layer/norm.py:9-16) */
+int vidi_rmsnorm_f32(const float* x, float* y, int rows, int D, float eps, int round_bf16, void* stream);
+
+/* layout kernels */
+int vidi_patch_im2col(const void* images, void* out, int F, int S, int patch, int Kpad, void* stream);      /* K1 */
+int vidi_whisper_im2col1(const void* mel, void* out, int C, int mels, int T, void* stream);                /* K8 conv1 */
+int vidi_whisper_im2col2(const void* x, void* out, int C, int T, int d, void* stream);                     /* K8 conv2 */
+/* Conv2DPool: pad + bilinear + space_to_depth gather (mm_vision/pool.py:23-32, utils.py:134-150), K4 */
+int vidi_pool_s2d(const void* P, void* X, int F, int side, int d, int h, int w, int m, void* stream);
+int vidi_embed_gather(const int64_t* ids, const void* E, void* out, int T, int D, int vocab, float normalizer, void* stream);
+int vidi_sinusoid_split(const float* div_term, void* out, int rows, int i0, int l, int N, int D, void* stream); /* pos.py:18-26,48-56 */
+int vidi_split3(const float* x, void* out, int64_t rows, int D, int mode, void* stream);
+int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* attention */
+/* bidirectional flash attention for the towers (flash_attn_func via HF SiglipAttention / WhisperAttention), K3/K8 */
+int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,
+                    int dh, float scale, void* stream);
+/* split-KV cross attention, replaces flash_cross_attention_forward (lmm/dattn/xattn.py:141-263) as called from
+ * DattnGemma2Attention.forward_xattn (gemma.py:81-91).  Opart fp32 [splits,T,Hq,dh], LSE fp32 [splits,T,Hq]. */
+int vidi_xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
+                       int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
+                       void* stream);
+/* LSE merge of P partials into fp32 out [rows, dh] (replaces the reference's all-gather of full K/V: all_to_all.py:361).
+ * partial p = (rank p / splits_per_rank, split p % splits_per_rank) is at Opart + rank*rank_stride_o + split*rows*dh and
+ * LSE + rank*rank_stride_l + split*rows (strides in floats): the all-gathered per-rank [O | LSE] blocks merge in place. */
+int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per_rank, int64_t rank_stride_o,
+                     int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream);
+int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream);
+/* causal text self attention with soft-cap and sliding window (HF Gemma2Attention via gemma.py:165-175), K16 */
+int vidi_attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int Tq, int Tk, int pos0, int Hq,
+                   int Hkv, int dh, float scale, float softcap, int window, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

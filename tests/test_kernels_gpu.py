@@ -1,0 +1,276 @@
+"""Per-kernel parity of the sm_100a library (through the C ABI) against plain PyTorch fp32 / the oracle."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda"); g.manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g, device="cuda") * scale)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 256, 64, 256), (128, 64, 64, 64), (256, 128, 128, 128),
+    (300, 520, 288, 256), (300, 520, 288, 128), (77, 72, 1152, 64),
+    (1000, 1152, 640, 256), (2048, 4096, 3584, 256), (4096, 3584, 2048, 128),
+    (33, 1024, 512, 256), (5000, 4304, 1152, 256),
+])
+def test_gemm_plain(M, N, K, bn):
+    from vidi_b200 import ops
+    a = rnd(M, K, seed=1).to(BF); w = rnd(N, K, scale=0.05, seed=2).to(BF)
+    out = ops.gemm(a, w, block_n=bn)
+    ref = a.float() @ w.float().t()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+    assert float((out.float() - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 1e-2
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
+def test_gemm_epilogues(act):
+    from vidi_b200 import ops
+    M, N, K = 515, 712, 264
+    a = rnd(M, K, seed=3).to(BF); w = rnd(N, K, scale=0.1, seed=4).to(BF)
+    bias = rnd(N, seed=5).float()
+    res = rnd(M, N, seed=6).to(BF)
+    out = ops.gemm(a, w, bias=bias, residual=res, act=act, act_param=3.0)
+    x = a.float() @ w.float().t() + bias
+    if act == 1: x = F.gelu(x)
+    elif act == 2: x = F.gelu(x, approximate="tanh")
+    elif act == 3: x = 3.0 * torch.tanh(x / 3.0)
+    elif act == 4: x = F.silu(x)
+    ref = x + res.float()
+    assert rel_err(out, ref) < 6e-3
+    # fp32 output, pos-emb style residual (row % res_mod)
+    pos = rnd(100, N, seed=7).to(BF)
+    out32 = ops.gemm(a, w, bias=bias, residual=pos, res_mod=100, out_fp32=True)
+    ref32 = a.float() @ w.float().t() + bias + pos.float()[torch.arange(M, device="cuda") % 100]
+    assert out32.dtype == torch.float32 and rel_err(out32, ref32) < 2e-3
+
+
+@pytest.mark.parametrize("glu", [1, 2])
+def test_gemm_glu(glu):
+    from vidi_b200 import ops
+    from vidi_b200.weights import pack_glu
+    M, I, K = 700, 1024, 512
+    a = rnd(M, K, seed=8).to(BF)
+    wg = rnd(I, K, scale=0.05, seed=9).to(BF); wu = rnd(I, K, scale=0.05, seed=10).to(BF)
+    wp = pack_glu(wg, wu, 256)
+    out = ops.gemm(a, wp, glu=glu, block_n=256)
+    g = a.float() @ wg.float().t(); u = a.float() @ wu.float().t()
+    ref = (F.gelu(g, approximate="tanh") if glu == 1 else F.silu(g)) * u
+    assert out.shape == (M, I) and rel_err(out, ref) < 8e-3
+
+
+def test_gemm_strided_views():
+    from vidi_b200 import ops
+    big = rnd(400, 1024, seed=11).to(BF)
+    a = big[:, 256:768]                      # lda = 1024, K = 512
+    w = rnd(384, 512, scale=0.05, seed=12).to(BF)
+    outbuf = torch.zeros(400, 1024, device="cuda", dtype=BF)
+    ops.gemm(a, w, out=outbuf[:, 128:512])
+    assert rel_err(outbuf[:, 128:512], a.float() @ w.float().t()) < 6e-3
+    assert float(outbuf[:, :128].abs().max()) == 0 and float(outbuf[:, 512:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("D", [3584, 512, 1152, 4096])
+def test_rmsnorm(D):
+    from vidi_b200 import ops
+    x = rnd(1001, D, scale=3.0, seed=13).to(BF); w = rnd(D, scale=0.1, seed=14).to(BF)
+    for add_one in (True, False):
+        y = ops.rmsnorm(x, w, 1e-6, add_one)
+        xf = x.float(); xh = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+        ref = xh * ((1 + w.float()) if add_one else w.float())
+        assert rel_err(y, ref) < 4e-3
+
+
+@pytest.mark.parametrize("post_mode,next_add_one", [(1, True), (0, False)])
+def test_residual_norm(post_mode, next_add_one):
+    from vidi_b200 import ops
+    D = 3584
+    x = rnd(777, D, seed=15).to(BF); y = rnd(777, D, scale=2.0, seed=16).to(BF)
+    wp = rnd(D, scale=0.1, seed=17).to(BF); wn = rnd(D, scale=0.1, seed=18).to(BF)
+    x0 = x.clone(); h = torch.empty_like(x)
+    ops.residual_norm(x, y, wp, wn, h, 1e-6, post_mode, next_add_one)
+    yf = y.float()
+    if post_mode:
+        yf = (yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-6) * (1 + wp.float())).to(BF).float()
+    xr = (x0.float() + yf).to(BF)
+    assert rel_err(x, xr) < 4e-3
+    xf = xr.float(); hr = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * ((1 + wn.float()) if next_add_one else wn.float())
+    assert rel_err(h, hr) < 5e-3
+
+
+@pytest.mark.parametrize("D", [1152, 1280, 288])
+def test_layernorm(D):
+    from vidi_b200 import ops
+    x = (rnd(999, D, scale=2.0, seed=19) + 0.5).to(BF)
+    w = (1 + rnd(D, scale=0.1, seed=20)).float(); b = rnd(D, scale=0.1, seed=21).float()
+    y = ops.layernorm(x, w, b, 1e-6)
+    assert rel_err(y, F.layer_norm(x.float(), (D,), w, b, 1e-6)) < 4e-3
+
+
+def test_mm_finish_matches_oracle_algebra():
+    from vidi_b200 import ops
+    D, Fr, hp, wp = 512, 5, 14, 14
+    rows = Fr * hp * wp
+    proj = rnd(rows, D, scale=2.0, seed=22).to(BF)
+    w_mod = (1 + rnd(D, scale=0.1, seed=23)).to(BF); w_llm = ((1 + rnd(D, scale=0.1, seed=24)) * 0.029).to(BF)
+    th, tw, tt = rnd(hp, D, seed=25).float().contiguous(), rnd(wp, D, seed=26).float().contiguous(), rnd(Fr + 3, D, seed=27).float().contiguous()
+    nrm = float(torch.tensor(D ** 0.5, dtype=BF).float())
+    out, mask = ops.mm_finish(proj, w_mod, w_llm, [th, tw, tt], [wp, 1, hp * wp], [hp, wp, 1 << 30], [0, 0, 2], 0, True, nrm, 1e-5)
+    xf = proj.float(); x = w_mod.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5))
+    x = x.view(Fr, hp, wp, D) + th[None, :, None] + tw[None, None, :] + tt[2:2 + Fr][:, None, None]
+    x = x.view(rows, D)
+    ref = w_llm.float() * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)) * nrm
+    assert bool(mask.all()) and rel_err(out, ref) < 8e-3
+    out0, mask0 = ops.mm_finish(proj, w_mod, w_llm, [th, tw, tt], [wp, 1, hp * wp], [hp, wp, 1 << 30], [0, 0, 2], 0, False, nrm, 1e-5)
+    assert not bool(mask0.any()) and float(out0.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ layout kernels vs the oracle
+def test_patch_im2col_and_conv():
+    from vidi_b200 import ops
+    img = rnd(3, 3, 378, 378, seed=28).clamp(-1, 1).to(BF)
+    w = rnd(64, 3, 14, 14, scale=0.05, seed=29).to(BF)
+    A = ops.patch_im2col(img, 14, 640)
+    wp = torch.zeros(64, 640, device="cuda", dtype=BF); wp[:, :588] = w.reshape(64, 588)
+    out = ops.gemm(A, wp)
+    ref = F.conv2d(img.float(), w.float(), stride=14).flatten(2).transpose(1, 2).reshape(-1, 64)
+    assert rel_err(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("hw", [(28, 28), (20, 20), (10, 10), (16, 12)])
+def test_pool_s2d(hw):
+    from vidi_b200 import ops
+    from oracle import vidi15_ref as R
+    Fr, side, d = 3, 27, 64
+    P = rnd(Fr, side * side, d, seed=30).to(BF)
+    X = ops.pool_s2d(P, Fr, side, hw[0], hw[1], 2)
+    feats = P.float().cpu().reshape(Fr, side, side, d).permute(0, 3, 1, 2)
+    ref = R.conv2d_pool(feats, hw, 2).permute(0, 2, 3, 1)                       # [F,h',w', c*4+q]
+    ref = ref.reshape(Fr, hw[0] // 2, hw[1] // 2, d, 4).permute(0, 1, 2, 4, 3).reshape(-1, 4 * d)   # -> q*d+c
+    assert rel_err(X.cpu(), ref) < 5e-3
+
+
+def test_whisper_im2col():
+    from vidi_b200 import ops
+    Cn, mels, T, d = 2, 128, 3000, 64
+    mel = rnd(Cn, mels, T, seed=31).to(BF)
+    w1 = rnd(d, mels, 3, scale=0.05, seed=32).to(BF)
+    A1 = ops.whisper_im2col1(mel)
+    y1 = ops.gemm(A1, w1.permute(0, 2, 1).reshape(d, 3 * mels).contiguous())
+    ref1 = F.conv1d(mel.float(), w1.float(), padding=1).permute(0, 2, 1).reshape(-1, d)
+    assert rel_err(y1, ref1) < 6e-3
+    w2 = rnd(d, d, 3, scale=0.05, seed=33).to(BF)
+    A2 = ops.whisper_im2col2(y1, Cn, T)
+    y2 = ops.gemm(A2, w2.permute(0, 2, 1).reshape(d, 3 * d).contiguous())
+    ref2 = F.conv1d(y1.float().view(Cn, T, d).permute(0, 2, 1), w2.float(), stride=2, padding=1).permute(0, 2, 1).reshape(-1, d)
+    assert rel_err(y2, ref2) < 6e-3
+
+
+def test_embed_gather_and_pos_split():
+    from vidi_b200 import ops
+    from oracle import vidi15_ref as R
+    E = rnd(1000, 512, scale=0.02, seed=34).to(BF)
+    ids = torch.tensor([2, 5, 999, 0, 17], device="cuda")
+    out = ops.embed_gather(ids, E, 22.625)
+    assert torch.equal(out, (E[ids].float() * 22.625).to(BF))
+    # split-precision positional MLP ~ fp32 accuracy
+    D, l, N = 512, 37, 10000
+    div = torch.exp(torch.arange(0, D, 2, dtype=torch.float) * -(math.log(10000.0) / D)).cuda()
+    A = ops.sinusoid_split(div, l, 0, l, N, D)
+    pe_ref = R.sinusoid(torch.arange(l, dtype=torch.float) / (l - 1) * (N - 1), D)
+    pe = (A[:, :D].float() + A[:, 2 * D:].float()).cpu()
+    assert float((pe - pe_ref).abs().max()) < 2e-3        # sin/cos of large arguments: device vs host libm
+    W = rnd(D, D, scale=0.03, seed=35).float()
+    Wp = ops.split3(W.contiguous(), 1)
+    y = ops.gemm(A, Wp, out_fp32=True)
+    ref = (A[:, :D].float() + A[:, 2 * D:].float()) @ W.t()
+    assert rel_err(y, ref) < 3e-5
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (1, 100, 2, 72), (2, 64, 2, 64)])
+def test_attn_dense(B, S, H, dh):
+    from vidi_b200 import ops
+    d = H * dh
+    qkv = rnd(B * S, 3 * d, seed=36).to(BF)
+    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5)
+    q, k, v = [t.float().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, d)
+    assert rel_err(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("T,N,Hq,Hkv,dh,cap,splits", [
+    (32, 5000, 16, 8, 256, 50.0, 7), (12, 300, 4, 2, 256, 50.0, 3), (40, 2048, 32, 8, 128, 0.0, 4),
+    (33, 1000, 16, 8, 256, 50.0, 1), (5, 31, 4, 2, 256, 50.0, 2),
+])
+def test_xattn_splitkv_and_merge(T, N, Hq, Hkv, dh, cap, splits):
+    from vidi_b200 import ops
+    q = rnd(T, Hq * dh, seed=37).to(BF)
+    kv = rnd(N, 2 * Hkv * dh, seed=38).to(BF)
+    k, v = kv[:, :Hkv * dh], kv[:, Hkv * dh:]
+    mask = torch.ones(N, device="cuda", dtype=torch.uint8); mask[N // 3: N // 3 + 5] = 0
+    scale = dh ** -0.5
+    op, lse = ops.xattn_splitkv(q, k, v, mask, Hq, Hkv, dh, scale, cap, splits)
+    out = torch.zeros(T * Hq, dh, device="cuda")
+    ops.xattn_merge(op, lse, out)
+    qh = q.float().view(T, Hq, dh).transpose(0, 1)
+    kh = k.float().reshape(N, Hkv, dh).transpose(0, 1).repeat_interleave(Hq // Hkv, 0)
+    vh = v.float().reshape(N, Hkv, dh).transpose(0, 1).repeat_interleave(Hq // Hkv, 0)
+    s = qh @ kh.transpose(-1, -2) * scale
+    if cap > 0: s = cap * torch.tanh(s / cap)
+    s = s.masked_fill(mask[None, None, :] == 0, float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(0, 1).reshape(T * Hq, dh)
+    assert rel_err(out, ref) < 8e-3
+    # accumulate + gate
+    ops.xattn_merge(op, lse, out, gate=0.5, accumulate=True)
+    assert rel_err(out, 1.5 * ref) < 8e-3
+    # merging the partials in two groups (== two ranks) then merging again must agree
+    if splits >= 2:
+        lse_all = torch.logsumexp(lse.view(splits, -1), 0)
+        sref = torch.logsumexp(s, -1).transpose(0, 1).reshape(-1)
+        assert float((lse_all - sref).abs().max()) < 2e-2
+
+
+def test_rope_and_attn_text():
+    from vidi_b200 import ops
+    from oracle import vidi15_ref as R
+    T, Hq, Hkv, dh = 37, 4, 2, 256
+    qd, kd = Hq * dh, Hkv * dh
+    qkv = rnd(T, qd + 2 * kd, seed=39).to(BF)
+    ref_in = qkv.clone()
+    inv = (1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.float) / dh))).cuda()
+    ops.rope_inplace(qkv, 0, Hq, dh, inv)
+    ops.rope_inplace(qkv, qd, Hkv, dh, inv)
+    cos, sin = R.rope_cos_sin(T, dh, 10000.0)
+    qr = R.apply_rope(ref_in[:, :qd].float().cpu().view(T, Hq, dh).transpose(0, 1), cos, sin)
+    kr = R.apply_rope(ref_in[:, qd:qd + kd].float().cpu().view(T, Hkv, dh).transpose(0, 1), cos, sin)
+    assert rel_err(qkv[:, :qd].cpu().view(T, Hq, dh).transpose(0, 1), qr) < 6e-3
+    for window in (0, 8):
+        out = ops.attn_text(qkv[:, :qd], qkv[:, qd:qd + kd], qkv[:, qd + kd:], 0, Hq, Hkv, dh, 1 / 16, 50.0, window)
+        i = torch.arange(T)
+        allowed = i[None, :] <= i[:, None]
+        if window: allowed &= (i[:, None] - i[None, :] < window)
+        bias = torch.zeros(T, T).masked_fill(~allowed, float("-inf"))
+        vh = ref_in[:, qd + kd:].float().cpu().view(T, Hkv, dh).transpose(0, 1)
+        ref = R.attend(qkv[:, :qd].float().cpu().view(T, Hq, dh).transpose(0, 1),
+                       qkv[:, qd:qd + kd].float().cpu().view(T, Hkv, dh).transpose(0, 1), vh, 1 / 16, 50.0, bias)
+        assert rel_err(out.cpu(), ref) < 5e-3

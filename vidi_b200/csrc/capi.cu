@@ -1,0 +1,120 @@
+// extern "C" surface of libvidi_b200.so (declared in include/vidi_b200.h).  Thin forwarding layer: validates nothing
+// beyond what the launchers check, counts launches, never synchronises.
+#include <atomic>
+
+#include "../../include/vidi_b200.h"
+#include "common.cuh"
+
+namespace vb {
+const char* last_error();
+int gemm_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
+              int, int, float, int, int, int, cudaStream_t);
+int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, int, float, cudaStream_t);
+int residual_norm(void*, int64_t, const void*, int64_t, const void*, const void*, void*, int64_t, int, int, float, int, int,
+                  cudaStream_t);
+int layernorm(const void*, int64_t, const float*, const float*, void*, int64_t, int, int, float, cudaStream_t);
+int mm_finish(const void*, int64_t, const void*, const void*, const float* const*, const int*, const int*, const int*, int,
+              int, int, float, void*, int64_t, uint8_t*, int, int, float, cudaStream_t);
+int rmsnorm_f32(const float*, float*, int, int, float, int, cudaStream_t);
+int patch_im2col(const void*, void*, int, int, int, int, cudaStream_t);
+int whisper_im2col1(const void*, void*, int, int, int, cudaStream_t);
+int whisper_im2col2(const void*, void*, int, int, int, cudaStream_t);
+int pool_s2d(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int embed_gather(const int64_t*, const void*, void*, int, int, int, float, cudaStream_t);
+int sinusoid_split(const float*, void*, int, int, int, int, int, cudaStream_t);
+int split3(const float*, void*, int64_t, int, int, cudaStream_t);
+int cast_f32_bf16(const float*, void*, int64_t, cudaStream_t);
+int attn_dense(const void*, int64_t, int, int, int, void*, int64_t, int, int, int, int, float, cudaStream_t);
+int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int, float,
+                  float, float*, float*, cudaStream_t);
+int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int, float, int, float*, cudaStream_t);
+int rope_inplace(void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
+int attn_text(const void*, int64_t, const void*, const void*, int64_t, int, int, int, int, int, int, float, float, int, float*,
+              cudaStream_t);
+}  // namespace vb
+
+static std::atomic<int64_t> g_launches{0};
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define COUNT(expr) (g_launches.fetch_add(1, std::memory_order_relaxed), (expr))
+
+extern "C" {
+
+const char* vidi_last_error(void) { return vb::last_error(); }
+int vidi_abi_version(void) { return 1; }
+int64_t vidi_launch_count(void) { return g_launches.load(); }
+void vidi_reset_launch_count(void) { g_launches.store(0); }
+
+int vidi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                   const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                   int out_fp32, int glu, int block_n, void* stream) {
+    return COUNT(vb::gemm_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, out_fp32, glu,
+                               block_n, ST(stream)));
+}
+int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
+                 float out_scale, void* stream) {
+    return COUNT(vb::rmsnorm(x, ldx, w, y, ldy, rows, D, eps, add_one, out_scale, ST(stream)));
+}
+int vidi_residual_norm(void* x, int64_t ldx, const void* y, int64_t ldy, const void* w_post, const void* w_next, void* h,
+                       int64_t ldh, int rows, int D, float eps, int post_mode, int next_add_one, void* stream) {
+    return COUNT(vb::residual_norm(x, ldx, y, ldy, w_post, w_next, h, ldh, rows, D, eps, post_mode, next_add_one, ST(stream)));
+}
+int vidi_layernorm(const void* x, int64_t ldx, const float* w, const float* b, void* y, int64_t ldy, int rows, int D,
+                   float eps, void* stream) {
+    return COUNT(vb::layernorm(x, ldx, w, b, y, ldy, rows, D, eps, ST(stream)));
+}
+int vidi_mm_finish(const void* proj, int64_t ldp, const void* w_mod, const void* w_llm, const float* const* tabs,
+                   const int* divs, const int* mods, const int* offs, int ntab, int n_offset, int sample_valid,
+                   float normalizer, void* out, int64_t ldo, uint8_t* mask, int rows, int D, float eps, void* stream) {
+    return COUNT(vb::mm_finish(proj, ldp, w_mod, w_llm, tabs, divs, mods, offs, ntab, n_offset, sample_valid, normalizer, out,
+                               ldo, mask, rows, D, eps, ST(stream)));
+}
+int vidi_rmsnorm_f32(const float* x, float* y, int rows, int D, float eps, int round_bf16, void* stream) {
+    return COUNT(vb::rmsnorm_f32(x, y, rows, D, eps, round_bf16, ST(stream)));
+}
+int vidi_patch_im2col(const void* images, void* out, int F, int S, int patch, int Kpad, void* stream) {
+    return COUNT(vb::patch_im2col(images, out, F, S, patch, Kpad, ST(stream)));
+}
+int vidi_whisper_im2col1(const void* mel, void* out, int C, int mels, int T, void* stream) {
+    return COUNT(vb::whisper_im2col1(mel, out, C, mels, T, ST(stream)));
+}
+int vidi_whisper_im2col2(const void* x, void* out, int C, int T, int d, void* stream) {
+    return COUNT(vb::whisper_im2col2(x, out, C, T, d, ST(stream)));
+}
+int vidi_pool_s2d(const void* P, void* X, int F, int side, int d, int h, int w, int m, void* stream) {
+    return COUNT(vb::pool_s2d(P, X, F, side, d, h, w, m, ST(stream)));
+}
+int vidi_embed_gather(const int64_t* ids, const void* E, void* out, int T, int D, int vocab, float normalizer, void* stream) {
+    return COUNT(vb::embed_gather(ids, E, out, T, D, vocab, normalizer, ST(stream)));
+}
+int vidi_sinusoid_split(const float* div_term, void* out, int rows, int i0, int l, int N, int D, void* stream) {
+    return COUNT(vb::sinusoid_split(div_term, out, rows, i0, l, N, D, ST(stream)));
+}
+int vidi_split3(const float* x, void* out, int64_t rows, int D, int mode, void* stream) {
+    return COUNT(vb::split3(x, out, rows, D, mode, ST(stream)));
+}
+int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+    return COUNT(vb::cast_f32_bf16(x, y, n, ST(stream)));
+}
+int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,
+                    int dh, float scale, void* stream) {
+    return COUNT(vb::attn_dense(qkv, ld, q_off, k_off, v_off, out, ldo, B, S, H, dh, scale, ST(stream)));
+}
+int vidi_xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
+                       int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
+                       void* stream) {
+    return COUNT(vb::xattn_splitkv(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, ST(stream)));
+}
+int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per_rank, int64_t rank_stride_o,
+                     int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream) {
+    return COUNT(vb::xattn_merge(Opart, LSE, P, splits_per_rank, rank_stride_o, rank_stride_l, rows, dh, gate, accumulate, out,
+                                 ST(stream)));
+}
+int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream) {
+    return COUNT(vb::rope_inplace(x, ld, col_off, T, heads, dh, inv_freq, pos0, ST(stream)));
+}
+int vidi_attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int Tq, int Tk, int pos0, int Hq,
+                   int Hkv, int dh, float scale, float softcap, int window, float* out, void* stream) {
+    return COUNT(vb::attn_text(Q, ldq, K, V, ldkv, Tq, Tk, pos0, Hq, Hkv, dh, scale, softcap, window, out, ST(stream)));
+}
+
+}  // extern "C"

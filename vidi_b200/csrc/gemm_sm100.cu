@@ -1,0 +1,342 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//
+//   * A and W are both K-major (nn.Linear layout: y = x W^T), moved global->shared by TMA
+//     (cp.async.bulk.tensor, 128-byte swizzle), 4-stage mbarrier ring.
+//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BLOCK_N, K=16) issued by one elected thread,
+//     fp32 accumulators live in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i
+//     overlaps the main loop of tile i+1.
+//   * Epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns), apply bias / activation /
+//     GeGLU / residual / soft-cap in fp32, and store bf16 (or fp32) rows with 128-bit stores.
+//   * One CTA per SM (grid = min(#tiles, #SMs)), static round-robin over a grouped tile order that
+//     keeps G m-blocks of A resident in L2 while W streams.
+//
+// This one kernel family serves every dense contraction on the Vidi prefill path (SURVEY.md 2.2
+// K1,K2,K5,K8,K9,K12,K13,K14,K17,K18).
+#include "common.cuh"
+
+namespace vb {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_SOFTCAP = 3, ACT_SILU = 4 };
+enum Glu : int { GLU_NONE = 0, GLU_GELU_TANH = 1, GLU_SILU = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    void* C;            // bf16 or fp32, row stride ldc (elements)
+    int64_t ldc;
+    const float* bias;  // [N] fp32 or null
+    const __nv_bfloat16* residual;  // [M, ldr] or null; added after activation
+    int64_t ldr;
+    int res_mod;        // > 0: residual row = row % res_mod (position-embedding add)
+    int act;
+    float act_param;    // soft-cap value
+    int out_fp32;
+    int glu;            // GLU_*: W rows are packed per tile as [BLOCK_N/2 gate | BLOCK_N/2 up]; C has N/2 columns
+    int group_m;
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-7 epilogue
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                     : (2 * BLOCK_N <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gm = min(group_m, num_m - first_m);
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % gm;
+    n_blk = r / gm;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;                       // [kStages]   TMA -> MMA
+    uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]   MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]         MMA -> epilogue
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]         epilogue -> MMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                                m_blk * BLOCK_M, kEvictNormal);
+                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K,
+                                n_blk * BLOCK_N, kEvictNormal);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+                    const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance 16 elements = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr>>4) field
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                      // == warp % 4: TMEM lane quarter this warp may access
+        const int row_in_tile = ew * 32 + lane_id();
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int out_cols_total = p.glu ? p.N / 2 : p.N;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + row_in_tile;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
+            if (p.glu) {
+                constexpr int HALF = BLOCK_N / 2;
+                const int col0 = n_blk * HALF;
+#pragma unroll 1
+                for (int c = 0; c < HALF; c += 16) {
+                    uint32_t g[16], u[16];
+                    tmem_ld_32x32b_x16(taddr + c, g);
+                    tmem_ld_32x32b_x16(taddr + HALF + c, u);
+                    tmem_ld_wait();
+                    if (row_ok && col0 + c < out_cols_total) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+                            float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
+                            if (p.glu == GLU_GELU_TANH) {
+                                g0 = gelu_tanh(g0); g1 = gelu_tanh(g1);
+                            } else {
+                                g0 = g0 / (1.0f + __expf(-g0)); g1 = g1 / (1.0f + __expf(-g1));
+                            }
+                            o[j] = pack_bf16(g0 * u0, g1 * u1);
+                        }
+                        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0 + c;
+                        if (col0 + c + 16 <= out_cols_total) {
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                __nv_bfloat162 pr = *reinterpret_cast<__nv_bfloat162*>(&o[j]);
+                                if (col0 + c + 2 * j < out_cols_total) dst[2 * j] = pr.x;
+                                if (col0 + c + 2 * j + 1 < out_cols_total) dst[2 * j + 1] = pr.y;
+                            }
+                        }
+                    }
+                }
+            } else {
+                const int col0 = n_blk * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + c, r);
+                    tmem_ld_wait();
+                    const int cbase = col0 + c;
+                    if (row_ok && cbase < p.N) {
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        const bool full = cbase + 32 <= p.N;
+                        if (p.bias) {
+                            if (full) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 b = *reinterpret_cast<const float4*>(p.bias + cbase + j);
+                                    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                                }
+                            } else {
+                                #pragma unroll
+                                for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += p.bias[cbase + j];
+                            }
+                        }
+                        if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        } else if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                        } else if (p.act == ACT_SOFTCAP) {
+                            const float inv = 1.0f / p.act_param;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = p.act_param * tanhf(v[j] * inv);
+                        } else if (p.act == ACT_SILU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+                        }
+                        if (p.residual) {
+                            const __nv_bfloat16* rp = p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr + cbase;
+                            if (full) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                                    float2 f;
+                                    f = unpack_bf16(q.x); v[j] += f.x; v[j + 1] += f.y;
+                                    f = unpack_bf16(q.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                                    f = unpack_bf16(q.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                                    f = unpack_bf16(q.w); v[j + 6] += f.x; v[j + 7] += f.y;
+                                }
+                            } else {
+                                #pragma unroll
+                                for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += __bfloat162float(rp[j]);
+                            }
+                        }
+                        if (p.out_fp32) {
+                            float* dst = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + cbase;
+                            if (full) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            } else {
+                                #pragma unroll
+                                for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = v[j];
+                            }
+                        } else {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + cbase;
+                            if (full) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8)
+                                    *reinterpret_cast<uint4*>(dst + j) =
+                                        make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                   pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                            } else {
+                                #pragma unroll
+                                for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = __float2bfloat16(v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BLOCK_N>
+static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M, num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = num_m * num_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_bf16_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+              const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
+              int glu, int block_n, cudaStream_t st) {
+    VB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    VB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: K/lda/ldw must be multiples of 8 (TMA 16B rows)");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_bf16: pointers must be 16B aligned");
+    VB_REQUIRE(ldc % 8 == 0, "gemm_bf16: ldc must be a multiple of 8");
+    VB_REQUIRE(!residual || ldr % 8 == 0, "gemm_bf16: ldr must be a multiple of 8");
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.res_mod = res_mod;
+    p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu; p.group_m = 16;
+    if (glu) VB_REQUIRE(N % block_n == 0, "gemm_bf16: GLU needs N %% block_n == 0 (packed gate|up tiles)");
+    if (block_n == 256) return launch_gemm<256>(A, lda, W, ldw, p, st);
+    if (block_n == 128) return launch_gemm<128>(A, lda, W, ldw, p, st);
+    if (block_n == 64) return launch_gemm<64>(A, lda, W, ldw, p, st);
+    VB_REQUIRE(false, "gemm_bf16: unsupported block_n %d", block_n);
+}
+
+}  // namespace vb

@@ -1,0 +1,280 @@
+"""Tensor-level wrappers over the C ABI.  torch is used for device memory and the current stream only;
+every computation is a kernel from ``libvidi_b200.so``.  All wrappers raise on CPU tensors."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import lib as _lib
+
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_SOFTCAP, ACT_SILU = 0, 1, 2, 3, 4
+GLU_NONE, GLU_GELU_TANH, GLU_SILU = 0, 1, 2
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("vidi_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _rowmajor(t: torch.Tensor) -> int:
+    """leading dimension (elements) of a 2-D row-major view; last dim must be contiguous."""
+    assert t.dim() == 2 and t.stride(1) == 1, f"need 2-D row-major, got {tuple(t.shape)} {t.stride()}"
+    return t.stride(0)
+
+
+def pick_block_n(M: int, N: int, glu: bool = False) -> int:
+    if glu:
+        return 256
+    if N >= 1024 or N % 256 == 0:
+        return 256
+    return 128 if N > 64 else 64
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         res_mod: int = 0, act: int = ACT_NONE, act_param: float = 0.0, out: Optional[torch.Tensor] = None,
+         out_fp32: bool = False, glu: int = GLU_NONE, block_n: Optional[int] = None) -> torch.Tensor:
+    """out[M,N(/2)] = epi(a[M,K] @ w[N,K]^T).  a,w bf16; bias fp32."""
+    L = _lib.load()
+    assert a.dtype == BF16 and w.dtype == BF16
+    M, K = a.shape
+    N, Kw = w.shape
+    assert K == Kw, (a.shape, w.shape)
+    n_out = N // 2 if glu else N
+    if block_n is None:
+        block_n = pick_block_n(M, N, bool(glu))
+    if out is None:
+        out = torch.empty(M, n_out, device=a.device, dtype=torch.float32 if out_fp32 else BF16)
+    assert out.shape == (M, n_out)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    if residual is not None:
+        assert residual.dtype == BF16
+    if M == 0:
+        return out
+    rc = L.vidi_gemm_bf16(_ptr(a), _rowmajor(a), _ptr(w), _rowmajor(w), _ptr(out), _rowmajor(out), M, N, K,
+                          _ptr(bias), _ptr(residual), _rowmajor(residual) if residual is not None else 0, res_mod,
+                          act, act_param, 1 if out.dtype == torch.float32 else 0, glu, block_n, _stream())
+    _lib.check(rc, "gemm_bf16")
+    return out
+
+
+def rmsnorm(x, w, eps, add_one: bool, out=None, out_scale: float = 1.0):
+    L = _lib.load()
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(L.vidi_rmsnorm(_ptr(x), _rowmajor(x), _ptr(w), _ptr(out), _rowmajor(out), rows, D, eps, int(add_one),
+                              out_scale, _stream()), "rmsnorm")
+    return out
+
+
+def residual_norm(x, y, w_post, w_next, h, eps, post_mode: int, next_add_one: bool):
+    """x += post(y); h = norm(x) (h may be None). In place on x."""
+    L = _lib.load()
+    rows, D = x.shape
+    _lib.check(L.vidi_residual_norm(_ptr(x), _rowmajor(x), _ptr(y), _rowmajor(y), _ptr(w_post), _ptr(w_next),
+                                    _ptr(h), _rowmajor(h) if h is not None else 0, rows, D, eps, post_mode,
+                                    int(next_add_one), _stream()), "residual_norm")
+    return x, h
+
+
+def layernorm(x, w, b, eps, out=None):
+    L = _lib.load()
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    assert w.dtype == torch.float32 and b.dtype == torch.float32
+    _lib.check(L.vidi_layernorm(_ptr(x), _rowmajor(x), _ptr(w), _ptr(b), _ptr(out), _rowmajor(out), rows, D, eps,
+                                _stream()), "layernorm")
+    return out
+
+
+def mm_finish(proj, w_mod, w_llm, tabs: Sequence[torch.Tensor], divs, mods, offs, n_offset: int, sample_valid: bool,
+              normalizer: float, eps: float, out=None, mask=None):
+    L = _lib.load()
+    rows, D = proj.shape
+    if out is None:
+        out = torch.empty_like(proj)
+    if mask is None:
+        mask = torch.empty(rows, device=proj.device, dtype=torch.uint8)
+    n = len(tabs)
+    for t in tabs:
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.shape[-1] == D
+    tp = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in tabs])
+    ia = lambda v: (C.c_int * max(n, 1))(*[int(x) for x in v])
+    _lib.check(L.vidi_mm_finish(_ptr(proj), _rowmajor(proj), _ptr(w_mod), _ptr(w_llm), tp, ia(divs), ia(mods), ia(offs),
+                                n, n_offset, int(sample_valid), normalizer, _ptr(out), _rowmajor(out), _ptr(mask),
+                                rows, D, eps, _stream()), "mm_finish")
+    return out, mask
+
+
+def rmsnorm_f32(x, eps, round_bf16: bool):
+    L = _lib.load()
+    rows, D = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.check(L.vidi_rmsnorm_f32(_ptr(x), _ptr(y), rows, D, eps, int(round_bf16), _stream()), "rmsnorm_f32")
+    return y
+
+
+def patch_im2col(images, patch: int, kpad: int):
+    L = _lib.load()
+    F_, Cc, S, S2 = images.shape
+    assert Cc == 3 and S == S2 and images.dtype == BF16 and images.is_contiguous()
+    side = S // patch
+    out = torch.empty(F_ * side * side, kpad, device=images.device, dtype=BF16)
+    _lib.check(L.vidi_patch_im2col(_ptr(images), _ptr(out), F_, S, patch, kpad, _stream()), "patch_im2col")
+    return out
+
+
+def whisper_im2col1(mel):
+    L = _lib.load()
+    Cn, mels, T = mel.shape
+    assert mel.dtype == BF16 and mel.is_contiguous()
+    out = torch.empty(Cn * T, 3 * mels, device=mel.device, dtype=BF16)
+    _lib.check(L.vidi_whisper_im2col1(_ptr(mel), _ptr(out), Cn, mels, T, _stream()), "whisper_im2col1")
+    return out
+
+
+def whisper_im2col2(x, Cn: int, T: int):
+    L = _lib.load()
+    d = x.shape[-1]
+    assert x.dtype == BF16 and x.is_contiguous() and x.numel() == Cn * T * d
+    out = torch.empty(Cn * (T // 2), 3 * d, device=x.device, dtype=BF16)
+    _lib.check(L.vidi_whisper_im2col2(_ptr(x), _ptr(out), Cn, T, d, _stream()), "whisper_im2col2")
+    return out
+
+
+def pool_s2d(P, F_: int, side: int, h: int, w: int, m: int):
+    L = _lib.load()
+    d = P.shape[-1]
+    assert P.dtype == BF16 and P.is_contiguous() and P.numel() == F_ * side * side * d
+    out = torch.empty(F_ * (h // m) * (w // m), m * m * d, device=P.device, dtype=BF16)
+    _lib.check(L.vidi_pool_s2d(_ptr(P), _ptr(out), F_, side, d, h, w, m, _stream()), "pool_s2d")
+    return out
+
+
+def embed_gather(ids, E, normalizer: float):
+    L = _lib.load()
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and E.dtype == BF16 and E.is_contiguous()
+    T = ids.numel()
+    out = torch.empty(T, E.shape[1], device=E.device, dtype=BF16)
+    _lib.check(L.vidi_embed_gather(_ptr(ids), _ptr(E), _ptr(out), T, E.shape[1], E.shape[0], normalizer, _stream()),
+               "embed_gather")
+    return out
+
+
+def sinusoid_split(div_term, rows: int, i0: int, l: int, N: int, D: int):
+    L = _lib.load()
+    assert div_term.dtype == torch.float32 and div_term.numel() == D // 2
+    out = torch.empty(rows, 3 * D, device=div_term.device, dtype=BF16)
+    _lib.check(L.vidi_sinusoid_split(_ptr(div_term), _ptr(out), rows, i0, l, N, D, _stream()), "sinusoid_split")
+    return out
+
+
+def split3(x, mode: int):
+    L = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    rows, D = x.shape
+    out = torch.empty(rows, 3 * D, device=x.device, dtype=BF16)
+    _lib.check(L.vidi_split3(_ptr(x), _ptr(out), rows, D, mode, _stream()), "split3")
+    return out
+
+
+def cast_bf16(x):
+    L = _lib.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.check(L.vidi_cast_f32_bf16(_ptr(x), _ptr(y), x.numel(), _stream()), "cast_f32_bf16")
+    return y
+
+
+def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None):
+    """qkv [B*S, 3*H*dh] with Q|K|V sections -> out [B*S, H*dh]."""
+    L = _lib.load()
+    d = H * dh
+    assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
+    if out is None:
+        out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
+    _lib.check(L.vidi_attn_dense(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale,
+                                 _stream()), "attn_dense")
+    return out
+
+
+def xattn_splits(n_keys: int, hkv: int, n_sms: int = 148) -> int:
+    """number of key splits so that splits*hkv CTAs cover the SMs ~2x, with >= 256 keys per split."""
+    if n_keys <= 0:
+        return 1
+    want = max(1, (2 * n_sms) // max(hkv, 1))
+    return max(1, min(want, (n_keys + 255) // 256))
+
+
+def xattn_splitkv(q, k, v, kmask, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, splits: int,
+                  opart=None, lse=None):
+    """q [T, Hq*dh]; k,v [N, *] views with row stride ld -> (opart [splits,T,Hq,dh] f32, lse [splits,T,Hq] f32)."""
+    L = _lib.load()
+    T = q.shape[0]
+    N = k.shape[0]
+    assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16
+    assert k.stride(0) == v.stride(0) or N == 0
+    if opart is None:
+        opart = torch.empty(splits, T, Hq, dh, device=q.device, dtype=torch.float32)
+        lse = torch.empty(splits, T, Hq, device=q.device, dtype=torch.float32)
+    _lib.check(L.vidi_xattn_splitkv(_ptr(q), _rowmajor(q), _ptr(k), _ptr(v), k.stride(0) if N else 8, _ptr(kmask), T, N,
+                                    Hq, Hkv, dh, splits, scale, softcap, _ptr(opart), _ptr(lse), _stream()),
+               "xattn_splitkv")
+    return opart, lse
+
+
+def xattn_merge(opart, lse, out, gate: float = 1.0, accumulate: bool = False, P=None, splits_per_rank=None,
+                rank_stride_o: int = 0, rank_stride_l: int = 0, rows=None, dh=None):
+    """Merge partials into out fp32 [rows, dh] (+=).  Default: opart [P, rows, dh], lse [P, rows] contiguous.
+    With explicit P / splits_per_rank / rank strides the partials may sit in an all-gathered flat buffer."""
+    L = _lib.load()
+    if P is None:
+        P = opart.shape[0]
+        dh = opart.shape[-1]
+        rows = lse.numel() // P
+        splits_per_rank = P
+        assert opart.is_contiguous() and lse.is_contiguous()
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    _lib.check(L.vidi_xattn_merge(_ptr(opart), _ptr(lse), P, splits_per_rank, rank_stride_o, rank_stride_l, rows, dh, gate,
+                                  int(accumulate), _ptr(out), _stream()), "xattn_merge")
+    return out
+
+
+def rope_inplace(x, col_off: int, heads: int, dh: int, inv_freq, pos0: int = 0):
+    L = _lib.load()
+    T = x.shape[0]
+    _lib.check(L.vidi_rope_inplace(_ptr(x), _rowmajor(x), col_off, T, heads, dh, _ptr(inv_freq), pos0, _stream()),
+               "rope_inplace")
+    return x
+
+
+def attn_text(q, k, v, pos0: int, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, window: int, out=None):
+    """q [Tq, Hq*dh] view, k/v [Tk, Hkv*dh] views -> fp32 [Tq, Hq*dh]."""
+    L = _lib.load()
+    Tq, Tk = q.shape[0], k.shape[0]
+    if out is None:
+        out = torch.empty(Tq, Hq * dh, device=q.device, dtype=torch.float32)
+    _lib.check(L.vidi_attn_text(_ptr(q), _rowmajor(q), _ptr(k), _ptr(v), _rowmajor(k), Tq, Tk, pos0, Hq, Hkv, dh, scale,
+                                softcap, window, _ptr(out), _stream()), "attn_text")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().vidi_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.load().vidi_reset_launch_count()
