@@ -1,0 +1,118 @@
+"""End-to-end parity: CUDA engine (through the C ABI) vs the fp32 CPU oracle on the same seeded inputs.
+
+Tolerances (bf16 engine vs fp32 oracle; stated per SURVEY.md 8c):
+  * stream activations / K,V per layer: relative L2 <= 2e-2
+  * final logits (after the 30*tanh soft-cap): max-abs <= 0.25 and relative L2 <= 3e-2
+  * greedy token ids identical wherever the oracle's top-1 margin exceeds the logit tolerance
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def build(cfg, seed=1234):
+    from oracle import synth
+    from vidi_b200.engine import Vidi15Engine
+    sd = synth.make_state_dict(cfg, seed=seed)
+    # the engine sees bf16 weights; the oracle sees the same bf16-rounded values in fp32
+    sd_r = {k: (v if "mm_rand_pos" in k else v.to(BF).float()) for k, v in sd.items()}
+    eng = Vidi15Engine(cfg, {k: v.clone() for k, v in sd_r.items()}, device="cuda")
+    return sd_r, eng
+
+
+def run_case(cfg, n_frames, n_chunks, n_text, audio_size=None, check_stages=True):
+    from oracle import synth, vidi15_ref as R
+    sd, eng = build(cfg)
+    ids, images, mels, asz = synth.make_inputs(cfg, n_frames, n_chunks, n_text=n_text, audio_size=audio_size)
+    images = images.to(BF).float(); mels = mels.to(BF).float()          # both sides see bf16-representable inputs
+    ref_logits, inter = R.prefill(sd, cfg, ids, images, mels, asz, normalizer_dtype=BF, return_intermediates=True)
+    ids_dev = R.strip_image_token(ids).cuda()
+    logits, st = eng.prefill(ids_dev, images.cuda().to(BF), mels.cuda().to(BF), asz, return_state=True)
+    torch.cuda.synchronize()
+    n_img, n_aud = inter["image_embeds"].shape[0], inter["audio_embeds"].shape[0]
+    assert st["streams"].shape[0] == n_img + n_aud
+    if check_stages:
+        nrm = R.normalizer(cfg, BF)
+        kv0 = st["kv"][0]
+        kd = cfg.llm.kv_dim
+        K0 = torch.cat([inter["kv"][0][0][0], inter["kv"][0][1][0]], 0)
+        V0 = torch.cat([inter["kv"][0][0][1], inter["kv"][0][1][1]], 0)
+        assert rel(kv0[:, :kd], K0) < 2e-2, ("K layer0", rel(kv0[:, :kd], K0))
+        assert rel(kv0[:, kd:], V0) < 2e-2, ("V layer0", rel(kv0[:, kd:], V0))
+        Ll = cfg.llm.layers - 1
+        KL = torch.cat([inter["kv"][Ll][0][0], inter["kv"][Ll][1][0]], 0)
+        assert rel(st["kv"][Ll][:, :kd], KL) < 3e-2, ("K last", rel(st["kv"][Ll][:, :kd], KL))
+    err = float((logits.cpu() - ref_logits).abs().max())
+    assert rel(logits, ref_logits) < 3e-2, rel(logits, ref_logits)
+    assert err < 0.25, err
+    top2 = ref_logits.topk(2, -1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert torch.equal(logits.cpu().argmax(-1)[confident], ref_logits.argmax(-1)[confident])
+    return logits, ref_logits
+
+
+def test_prefill_mini_config1_shape():
+    """BASELINE config 1 shape (8 frames, 1 audio chunk) at mini dims."""
+    from vidi_b200.config import vidi15_mini
+    run_case(vidi15_mini(), n_frames=8, n_chunks=1, n_text=24)
+
+
+def test_prefill_mini_resized_featuremap():
+    """Force the > max_image_tokens branch (bilinear shrink, utils.py:152-171) with a small cap."""
+    import dataclasses
+    from vidi_b200.config import vidi15_mini
+    cfg = dataclasses.replace(vidi15_mini(), max_image_tokens=400)      # 6 frames * 784 > 1600 -> 16x16 maps
+    assert cfg.image_hw(6) != (28, 28)
+    run_case(cfg, n_frames=6, n_chunks=1, n_text=9, check_stages=False)
+
+
+def test_prefill_ragged_audio_and_odd_text():
+    from vidi_b200.config import vidi15_mini
+    run_case(vidi15_mini(llm_layers=3), n_frames=3, n_chunks=2, n_text=33, audio_size=4321, check_stages=False)
+
+
+def test_prefill_true_dims_depth_cut():
+    """True 9B hidden sizes (3584 / 1152 / 1280, head dims 256 / 72 / 64), depth cut to keep the CPU oracle fast."""
+    from vidi_b200.config import vidi15_true_dims
+    run_case(vidi15_true_dims(llm_layers=2, vis_layers=2, aud_layers=1, vocab=4096), n_frames=2, n_chunks=1, n_text=16,
+             audio_size=400)
+
+
+def test_sharded_equals_single_rank_fake_multirank():
+    """Run the shard function for ranks 0..P-1 serially on one device and merge: must match the 1-rank result
+    (SURVEY.md section 4c).  Exercises ShardPlan offsets, global positional indices and the partial merge."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200 import ops
+    from vidi_b200.config import vidi15_mini
+    from vidi_b200.engine import make_plan
+    cfg = vidi15_mini()
+    sd, eng = build(cfg)
+    ids, images, mels, asz = synth.make_inputs(cfg, 5, 3, n_text=11, audio_size=7000)
+    images = images.cuda().to(BF); mels = mels.cuda().to(BF)
+    ids_dev = R.strip_image_token(ids).cuda()
+    full, st = eng.prefill(ids_dev, images, mels, asz, return_state=True)
+    world = 3
+    S_parts, kv_parts = [], []
+    for r in range(world):
+        eng.rank, eng.world = r, world
+        plan = make_plan(cfg, 5, 3, asz, r, world)
+        S, seg = eng.encode_streams(images[plan.f0:plan.f1], mels[plan.c0:plan.c1], plan)
+        S_parts.append((S.clone(), seg, plan))
+        kv_parts.append(eng.stream_pass(S))
+    eng.rank, eng.world = 0, 1
+    # stream rows of all ranks, re-ordered to [all image rows | all audio rows], must equal the 1-rank stream
+    img_rows = torch.cat([kv[:, seg[0][0]:seg[0][0] + seg[0][1]] for kv, (_, seg, _) in zip(kv_parts, S_parts)], 1)
+    aud_rows = torch.cat([kv[:, seg[1][0]:seg[1][0] + seg[1][1]] for kv, (_, seg, _) in zip(kv_parts, S_parts)], 1)
+    merged = torch.cat([img_rows, aud_rows], 1)
+    assert merged.shape == st["kv"].shape
+    assert rel(merged, st["kv"]) < 1e-2
+    seg_full = [(0, img_rows.shape[1], None, 1.0, img_rows.shape[1]), (img_rows.shape[1], aud_rows.shape[1], None, 1.0, aud_rows.shape[1])]
+    logits2 = eng.text_pass(ids_dev, merged.contiguous(), seg_full)
+    assert rel(logits2, full) < 1e-2

@@ -1,0 +1,99 @@
+"""Micro-benchmarks of the hot kernels (CUDA events, L2-flushed between iterations) next to the library bar
+(torch.matmul -> cuBLAS, flash-attn 2) the reference would run on the same B200.  Not the headline bench."""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from vidi_b200 import ops  # noqa: E402
+from vidi_b200.weights import pack_glu  # noqa: E402
+
+BF = torch.bfloat16
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, iters=8, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm_case(name, M, N, K, glu=0, bn=None):
+    a = torch.randn(M, K, device="cuda").to(BF)
+    w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
+    out = torch.empty(M, N // 2 if glu else N, device="cuda", dtype=BF)
+    t = timeit(lambda: ops.gemm(a, w, out=out, glu=glu, block_n=bn))
+    ref = torch.empty(M, N, device="cuda", dtype=BF)
+    t_ref = timeit(lambda: torch.matmul(a, w.t(), out=ref))
+    fl = 2.0 * M * N * K
+    print(json.dumps(dict(kernel="gemm", name=name, M=M, N=N, K=K, glu=glu, ms=round(t, 4), tflops=round(fl / t / 1e9, 1),
+                          cublas_ms=round(t_ref, 4), cublas_tflops=round(fl / t_ref / 1e9, 1))), flush=True)
+
+
+def xattn_case(T, N, splits=None):
+    Hq, Hkv, dh = 16, 8, 256
+    q = torch.randn(T, Hq * dh, device="cuda").to(BF)
+    kv = torch.randn(N, 2 * Hkv * dh, device="cuda").to(BF)
+    sp = splits or ops.xattn_splits(N, Hkv)
+    op = torch.empty(sp, T, Hq, dh, device="cuda"); ls = torch.empty(sp, T, Hq, device="cuda")
+    t = timeit(lambda: ops.xattn_splitkv(q, kv[:, :2048], kv[:, 2048:], None, Hq, Hkv, dh, 1 / 16, 50.0, sp, opart=op, lse=ls))
+    by = N * 8192
+    print(json.dumps(dict(kernel="xattn_splitkv", T=T, N=N, splits=sp, ms=round(t, 4), gbs=round(by / t / 1e6, 1))), flush=True)
+
+
+def dense_case(B, S, H, dh):
+    d = H * dh
+    qkv = torch.randn(B * S, 3 * d, device="cuda").to(BF)
+    out = torch.empty(B * S, d, device="cuda", dtype=BF)
+    t = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out))
+    fl = 4.0 * B * H * S * S * dh
+    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1))
+    try:
+        from flash_attn import flash_attn_func
+        q, k, v = [x.reshape(B, S, H, dh) for x in qkv.split(d, 1)]
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        t2 = timeit(lambda: flash_attn_func(q, k, v))
+        rec.update(fa2_ms=round(t2, 4), fa2_tflops=round(fl / t2 / 1e9, 1))
+    except Exception as ex:  # noqa: BLE001
+        rec["fa2"] = f"unavailable: {type(ex).__name__}"
+    print(json.dumps(rec), flush=True)
+
+
+def rownorm_case(rows, D):
+    x = torch.randn(rows, D, device="cuda").to(BF); y = torch.randn(rows, D, device="cuda").to(BF)
+    w = torch.randn(D, device="cuda").to(BF); h = torch.empty_like(x)
+    t = timeit(lambda: ops.residual_norm(x, y, w, w, h, 1e-6, 1, True))
+    print(json.dumps(dict(kernel="residual_norm", rows=rows, D=D, ms=round(t, 4), gbs=round(rows * D * 2 * 4 / t / 1e6, 1))), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "gemm"):
+        M = 15750
+        gemm_case("kv_proj", M, 4096, 3584)
+        gemm_case("v_o_fold", M, 3584, 2048)
+        gemm_case("gate_up_geglu", M, 28672, 3584, glu=1)
+        gemm_case("down", M, 3584, 14336)
+        gemm_case("vit_qkv", 64 * 729, 3456, 1152)
+        gemm_case("vit_fc1", 64 * 729, 4304, 1152)
+        gemm_case("vit_fc2", 64 * 729, 1152, 4304)
+        gemm_case("vit_out", 64 * 729, 1152, 1152)
+        gemm_case("square8k", 8192, 8192, 8192)
+        gemm_case("text_gateup", 32, 28672, 3584, glu=1)
+        gemm_case("text_down", 32, 3584, 14336)
+        gemm_case("text_down_bn64", 32, 3584, 14336, bn=64)
+    if which in ("all", "attn"):
+        xattn_case(32, 126000)
+        xattn_case(32, 16000)
+        dense_case(64, 729, 16, 72)
+        dense_case(16, 1500, 20, 64)
+        rownorm_case(126000, 3584)

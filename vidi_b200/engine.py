@@ -1,0 +1,332 @@
+"""Vidi1.5-9B prefill engine: host-side orchestration of the sm_100a kernels.
+
+Design: the image and audio streams are token-wise independent through all decoder
+layers (gemma.py:183-202 reads only the stream itself), so
+  1. the towers + projectors run per frame / per audio chunk               (encode_images / encode_audios)
+  2. ONE concatenated [N_img+N_aud, D] stream runs the whole layer stack, writing the per-layer
+     K||V cache [L, N, 2*kv_dim] and applying the diagonal V2V + GeGLU updates   (stream_pass)
+  3. the short text stream then runs its layers against that cache with the split-KV
+     cross-attention kernel; across GPUs only the (O, LSE) partials are exchanged  (text_pass)
+Frames / chunks / tokens are sharded contiguously over ranks (ShardPlan); the text stream is replicated.
+Nothing here computes on the CPU; torch supplies memory, streams and the NCCL all-gather only.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .weights import load_vidi15
+
+BF16 = torch.bfloat16
+BIG = 1 << 30
+
+
+@dataclass
+class ShardPlan:
+    """Contiguous partition of frames / audio chunks / stream tokens over ranks."""
+    rank: int
+    world: int
+    F: int
+    C: int
+    f0: int
+    f1: int
+    c0: int
+    c1: int
+    hw: tuple
+    tpf: int            # image tokens per frame
+    n_img_total: int
+    n_aud_total: int    # s2
+    s1: int
+    tpc: int            # audio tokens per chunk
+    a0: int             # first global audio token of this rank
+    a1: int
+
+    @property
+    def n_img(self) -> int:
+        return (self.f1 - self.f0) * self.tpf
+
+    @property
+    def n_aud(self) -> int:
+        return max(0, self.a1 - self.a0)
+
+
+def _split(n: int, world: int, rank: int):
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def make_plan(cfg, n_frames: int, n_chunks: int, audio_size: int, rank: int = 0, world: int = 1) -> ShardPlan:
+    hw = cfg.image_hw(n_frames) if n_frames else (28, 28)
+    m = cfg.mm_image_pool_size
+    tpf = (hw[0] // m) * (hw[1] // m)
+    f0, f1 = _split(n_frames, world, rank)
+    c0, c1 = _split(n_chunks, world, rank)
+    ratio = cfg.aud.max_source_positions / cfg.aud.nb_max_frames
+    s1 = int(math.floor(audio_size * ratio)) if n_chunks else 0
+    s1 = min(s1, n_chunks * cfg.aud.max_source_positions)
+    s2 = int(math.floor(s1 / cfg.mm_audio_pool_size))
+    assert cfg.aud.max_source_positions % cfg.mm_audio_pool_size == 0
+    tpc = cfg.aud.max_source_positions // cfg.mm_audio_pool_size
+    a0, a1 = min(c0 * tpc, s2), min(c1 * tpc, s2)
+    return ShardPlan(rank, world, n_frames, n_chunks, f0, f1, c0, c1, hw, tpf, n_frames * tpf, s2, s1, tpc, a0, a1)
+
+
+class Vidi15Engine:
+    def __init__(self, cfg, state_dict: dict, device="cuda", rank: int = 0, world: int = 1, group=None,
+                 pop_state_dict: bool = False, vit_chunk: int = 128, aud_chunk: int = 16):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vidi_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.rank, self.world, self.group = rank, world, group
+        self.W = load_vidi15(state_dict, cfg, self.device, ops, pop=pop_state_dict)
+        # torch.tensor(hidden**0.5, dtype=act): the normaliser is rounded to the activation dtype (gemma.py:353)
+        self.normalizer = float(torch.tensor(cfg.llm.hidden ** 0.5, dtype=BF16).float())
+        self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    # ------------------------------------------------------------------------------------------
+    # towers
+    # ------------------------------------------------------------------------------------------
+    def _tower_layer(self, x, L, B, S, heads, dh, eps, act):
+        h = ops.layernorm(x, L.ln1_w, L.ln1_b, eps)
+        qkv = ops.gemm(h, L.wqkv, bias=L.bqkv)
+        a = ops.attn_dense(qkv, B, S, heads, dh, dh ** -0.5)
+        ops.gemm(a, L.wo, bias=L.bo, residual=x, out=x)
+        h = ops.layernorm(x, L.ln2_w, L.ln2_b, eps, out=h)
+        m = ops.gemm(h, L.w1, bias=L.b1, act=act)
+        ops.gemm(m, L.w2, bias=L.b2, residual=x, out=x)
+        return x
+
+    def siglip(self, images: torch.Tensor) -> torch.Tensor:
+        """images [f,3,S,S] bf16 -> hidden_states[-2] [f*P, dv]  (siglip.py:29-34)."""
+        v, Wv = self.cfg.vis, self.W.vis
+        f = images.shape[0]
+        A = ops.patch_im2col(images, v.patch, Wv.kpad)
+        x = ops.gemm(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches)
+        del A
+        for L in Wv.layers:
+            x = self._tower_layer(x, L, f, v.patches, v.heads, v.head_dim, v.eps, ops.ACT_GELU_TANH)
+        return x
+
+    def whisper(self, mels: torch.Tensor) -> torch.Tensor:
+        """mels [c,128,3000] bf16 -> [c*1500, da]  (whisper.py:26-27)."""
+        a, Wa = self.cfg.aud, self.W.aud
+        c, T = mels.shape[0], mels.shape[2]
+        A1 = ops.whisper_im2col1(mels)
+        x1 = ops.gemm(A1, Wa.conv1_w, bias=Wa.conv1_b, act=ops.ACT_GELU_ERF)
+        del A1
+        A2 = ops.whisper_im2col2(x1, c, T)
+        del x1
+        x = ops.gemm(A2, Wa.conv2_w, bias=Wa.conv2_b, act=ops.ACT_GELU_ERF, residual=Wa.pos, res_mod=T // 2)
+        del A2
+        for L in Wa.layers:
+            x = self._tower_layer(x, L, c, T // 2, a.heads, a.head_dim, a.eps, ops.ACT_GELU_ERF)
+        return ops.layernorm(x, Wa.ln_w, Wa.ln_b, a.eps)
+
+    def pos_table(self, name: str, rows: int, i0: int, l: int, N: int) -> torch.Tensor:
+        """rms_norm(LearnablePosEmbd(...)) rows i0..i0+rows of l -> fp32 [rows, D]  (pos.py:41-58, norm.py:9-16)."""
+        assert l > 1, "LearnablePosEmbd asserts x.shape[dim] > 1 (pos.py:42)"
+        D, P = self.cfg.llm.hidden, self.W.pos[name]
+        if rows == 0:
+            return torch.zeros(1, D, device=self.device)
+        A = ops.sinusoid_split(self.W.div_term, rows, i0, l, N, D)
+        h = ops.gemm(A, P.w0, bias=P.b0, act=ops.ACT_GELU_ERF, out_fp32=True)
+        y = ops.gemm(ops.split3(h, 0), P.w2, bias=P.b2, out_fp32=True)
+        return ops.rmsnorm_f32(y, self.cfg.mm_eps, round_bf16=True)
+
+    def _project(self, x, proj):
+        h = ops.gemm(x, proj.w1, bias=proj.b1, act=ops.ACT_GELU_ERF)
+        return ops.gemm(h, proj.w2, bias=proj.b2)
+
+    def encode_images(self, images: torch.Tensor, plan: ShardPlan, sample_valid: bool = True):
+        """This rank's frames [f1-f0,3,S,S] bf16 -> (stream rows [n_img, D] already * sqrt(D), mask uint8)
+        (multimodal.py:156-208, gemma.py:353-355)."""
+        cfg, v = self.cfg, self.cfg.vis
+        D, m = cfg.llm.hidden, cfg.mm_image_pool_size
+        fl = plan.f1 - plan.f0
+        assert images.shape[0] == fl and images.dtype == BF16
+        h, w = plan.hw
+        proj = torch.empty(plan.n_img, D, device=self.device, dtype=BF16)
+        for s in range(0, fl, self.vit_chunk):
+            e = min(fl, s + self.vit_chunk)
+            P = self.siglip(images[s:e])
+            X = ops.pool_s2d(P, e - s, v.side, h, w, m)
+            del P
+            hid = ops.gemm(X, self.W.img_proj.w1, bias=self.W.img_proj.b1, act=ops.ACT_GELU_ERF)
+            ops.gemm(hid, self.W.img_proj.w2, bias=self.W.img_proj.b2, out=proj[s * plan.tpf:e * plan.tpf])
+            del X, hid
+        hp, wp = h // m, w // m
+        th = self.pos_table("h", hp, 0, hp, m)
+        tw = self.pos_table("w", wp, 0, wp, m)
+        tt = self.pos_table("t", fl, plan.f0, plan.F, cfg.mm_time_interval)
+        out, mask = ops.mm_finish(proj, self.W.img_norm, self.W.llm_norm, [th, tw, tt], [wp, 1, hp * wp], [hp, wp, BIG],
+                                  [0, 0, 0], 0, sample_valid, self.normalizer, cfg.mm_eps, out=proj)
+        return out, mask
+
+    def encode_audios(self, mels: torch.Tensor, plan: ShardPlan, sample_valid: bool = True):
+        """This rank's chunks [c1-c0,128,3000] bf16 -> (stream rows [n_aud, D], mask)  (multimodal.py:210-252)."""
+        cfg, a = self.cfg, self.cfg.aud
+        D, k = cfg.llm.hidden, cfg.mm_audio_pool_size
+        cl = plan.c1 - plan.c0
+        assert mels.shape[0] == cl and mels.dtype == BF16
+        n = plan.n_aud
+        feats = torch.empty(cl * a.max_source_positions, a.d_model, device=self.device, dtype=BF16)
+        for s in range(0, cl, self.aud_chunk):
+            e = min(cl, s + self.aud_chunk)
+            feats[s * a.max_source_positions:e * a.max_source_positions] = self.whisper(mels[s:e])
+        if n == 0:
+            return torch.empty(0, D, device=self.device, dtype=BF16), torch.empty(0, device=self.device, dtype=torch.uint8)
+        A = feats.view(-1)[: n * k * a.d_model].view(n, k * a.d_model)         # Conv1d(k=s=5) == reshape + GEMM
+        pooled = ops.gemm(A, self.W.aud_pool)
+        proj = self._project(pooled, self.W.aud_proj)
+        tt = self.pos_table("t", n, plan.a0, plan.n_aud_total, cfg.mm_time_interval)
+        return ops.mm_finish(proj, self.W.aud_norm, self.W.llm_norm, [tt], [1], [BIG], [0], 0, sample_valid,
+                             self.normalizer, cfg.mm_eps, out=proj)
+
+    # ------------------------------------------------------------------------------------------
+    # decoder: stream pass
+    # ------------------------------------------------------------------------------------------
+    def stream_pass(self, S: torch.Tensor, kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """S [n, D] (modified in place) -> K||V cache [L, n, 2*kv_dim] bf16.
+        Per layer (gemma.py:183-202 with Q5/Q6 of SURVEY 3.4 dropped): K||V = G(S,w_in) W_kv^T;
+        S += G(V W_o'^T, w_post); S += G(MLP(G(S,w_pre)), w_postff).  The last layer only needs K||V."""
+        c = self.cfg.llm
+        n, D = S.shape
+        Ls = self.W.layers
+        if kv is None:
+            kv = torch.empty(len(Ls), n, 2 * c.kv_dim, device=self.device, dtype=BF16)
+        if n == 0:
+            return kv
+        h = ops.rmsnorm(S, Ls[0].n_in, c.rms_eps, True)
+        y = torch.empty_like(S)
+        g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
+        for l, L in enumerate(Ls):
+            ops.gemm(h, L.wkv, out=kv[l])
+            if l == len(Ls) - 1:
+                break
+            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y)
+            ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
+            ops.gemm(h, L.wgu, glu=ops.GLU_GELU_TANH, out=g)
+            ops.gemm(g, L.wd, out=y)
+            ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
+        return kv
+
+    # ------------------------------------------------------------------------------------------
+    # decoder: text pass
+    # ------------------------------------------------------------------------------------------
+    def new_text_cache(self, max_len: int) -> dict:
+        c = self.cfg.llm
+        return dict(kv=torch.empty(c.layers, max_len, 2 * c.kv_dim, device=self.device, dtype=BF16), len=0)
+
+    def text_pass(self, ids: torch.Tensor, kv: torch.Tensor, seg: list, text_cache: Optional[dict] = None,
+                  logits_to_keep: int = 0) -> torch.Tensor:
+        """ids [Tq] int64 (sentinel already stripped) -> logits fp32 [Tq or k, vocab].
+        seg: list of (row0, n_rows, kmask or None, gate, n_total) describing the image / audio row ranges of the
+        local K||V cache.  (gemma.py:160-175, 185-192, 206-221, 236-238, 564-569)"""
+        c = self.cfg.llm
+        Tq = ids.numel()
+        qd, kd, dh = c.q_dim, c.kv_dim, c.head_dim
+        pos0 = 0
+        if text_cache is not None:
+            pos0 = text_cache["len"]
+            assert pos0 + Tq <= text_cache["kv"].shape[1], "text KV cache too small"
+        scale = c.query_pre_attn_scalar ** -0.5 if hasattr(c, "query_pre_attn_scalar") else dh ** -0.5
+        cap = getattr(c, "attn_softcap", 0.0) or 0.0
+        Ls = self.W.layers
+        H = ops.embed_gather(ids, self.W.embed, self.normalizer)
+        h = ops.rmsnorm(H, Ls[0].n_in, c.rms_eps, True)
+        rows = Tq * c.heads
+        # one flat fp32 buffer per layer holds every stream's [O | LSE] partials of this rank
+        splits = [ops.xattn_splits(-(-s[4] // self.world), c.kv_heads, self.n_sms) for s in seg]
+        sizes = [sp * rows * (dh + 1) for sp in splits]
+        flat = torch.empty(max(1, sum(sizes)), device=self.device, dtype=torch.float32)
+        gathered = torch.empty(self.world * flat.numel(), device=self.device, dtype=torch.float32) if self.world > 1 else flat
+        att = torch.empty(Tq, qd, device=self.device, dtype=torch.float32)
+        y = torch.empty(Tq, c.hidden, device=self.device, dtype=BF16)
+        for l, L in enumerate(Ls):
+            qkv = ops.gemm(h, L.wqkv)
+            if text_cache is not None:
+                tkv = text_cache["kv"][l]
+                tkv[pos0:pos0 + Tq].copy_(qkv[:, qd:])
+                kview, vview, Tk = tkv[:pos0 + Tq, :kd], tkv[:pos0 + Tq, kd:], pos0 + Tq
+                ops.rope_inplace(tkv[pos0:pos0 + Tq], 0, c.kv_heads, dh, self.W.inv_freq, pos0)
+            else:
+                krope = qkv[:, qd:].clone()
+                ops.rope_inplace(krope, 0, c.kv_heads, dh, self.W.inv_freq, pos0)
+                kview, vview, Tk = krope[:, :kd], krope[:, kd:], Tq
+            qrope = qkv[:, :qd].clone()
+            ops.rope_inplace(qrope, 0, c.heads, dh, self.W.inv_freq, pos0)
+            window = c.sliding_window if (hasattr(c, "sliding_window") and l % 2 == 0) else 0
+            ops.attn_text(qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, scale, cap, window, out=att)
+            off = 0
+            for (r0, nr, kmask, gate, _), sp, sz in zip(seg, splits, sizes):
+                op = flat[off:off + sp * rows * dh]
+                ls = flat[off + sp * rows * dh:off + sz]
+                kvl = kv[l]
+                ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
+                                  scale, cap, sp, opart=op, lse=ls)
+                off += sz
+            if self.world > 1:
+                torch.distributed.all_gather_into_tensor(gathered, flat, group=self.group)
+            off = 0
+            for (r0, nr, kmask, gate, _), sp, sz in zip(seg, splits, sizes):
+                ops.xattn_merge(gathered[off:], gathered[off + sp * rows * dh:], att, gate=gate, accumulate=True,
+                                P=self.world * sp, splits_per_rank=sp, rank_stride_o=flat.numel(),
+                                rank_stride_l=flat.numel(), rows=rows, dh=dh)
+                off += sz
+            a = ops.cast_bf16(att)
+            ops.gemm(a, L.wo, out=y)
+            h2 = torch.empty_like(H)
+            ops.residual_norm(H, y, L.n_post, L.n_preff, h2, c.rms_eps, 1, True)
+            g = ops.gemm(h2, L.wgu, glu=ops.GLU_GELU_TANH)
+            ops.gemm(g, L.wd, out=y)
+            w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else self.W.final_norm
+            ops.residual_norm(H, y, L.n_postff, w_next, h, c.rms_eps, 1, True)
+        if text_cache is not None:
+            text_cache["len"] = pos0 + Tq
+        hn = h if not logits_to_keep else h[-logits_to_keep:]
+        return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True)
+
+    # ------------------------------------------------------------------------------------------
+    # whole prefill for one sample
+    # ------------------------------------------------------------------------------------------
+    def encode_streams(self, images, mels, plan: ShardPlan, image_valid=True, audio_valid=True):
+        """-> (S [n_img+n_aud, D], seg list for text_pass)"""
+        parts, seg = [], []
+        r0 = 0
+        if images is not None:
+            X, mX = self.encode_images(images, plan, image_valid)
+            parts.append(X)
+            seg.append((r0, X.shape[0], mX if image_valid else None, 1.0 if image_valid else 0.0, plan.n_img_total))
+            r0 += X.shape[0]
+        if mels is not None:
+            A, mA = self.encode_audios(mels, plan, audio_valid)
+            parts.append(A)
+            seg.append((r0, A.shape[0], mA if audio_valid else None, 1.0 if audio_valid else 0.0, plan.n_aud_total))
+            r0 += A.shape[0]
+        if not parts:
+            return torch.empty(0, self.cfg.llm.hidden, device=self.device, dtype=BF16), seg
+        S = parts[0] if len(parts) == 1 else torch.cat(parts, 0)
+        return S, seg
+
+    @torch.no_grad()
+    def prefill(self, ids: torch.Tensor, images: Optional[torch.Tensor], mels: Optional[torch.Tensor], audio_size: int,
+                n_frames_total: Optional[int] = None, n_chunks_total: Optional[int] = None, logits_to_keep: int = 0,
+                text_cache: Optional[dict] = None, image_valid=True, audio_valid=True, return_state: bool = False):
+        """ids: [T] int64 device tensor without the -200 sentinel.  images / mels are THIS RANK's shard
+        (see make_plan) in bf16 on the device.  Returns logits fp32 [T or k, vocab]."""
+        F = n_frames_total if n_frames_total is not None else (images.shape[0] if images is not None else 0)
+        Cn = n_chunks_total if n_chunks_total is not None else (mels.shape[0] if mels is not None else 0)
+        plan = make_plan(self.cfg, F, Cn, audio_size or 0, self.rank, self.world)
+        S, seg = self.encode_streams(images, mels, plan, image_valid, audio_valid)
+        kv = self.stream_pass(S)
+        logits = self.text_pass(ids, kv, seg, text_cache=text_cache, logits_to_keep=logits_to_keep)
+        if return_state:
+            return logits, dict(kv=kv, seg=seg, plan=plan, streams=S)
+        return logits
