@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline bench: Vidi1.5-9B prefill multimodal tokens/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2p|c2|c1] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one full prefill of one synthetic video (SigLIP tower over F frames, Whisper encoder over C chunks,
+projectors, the 42-layer Dattn stream pass, the text pass, lm_head) with random-init weights of the true
+Vidi1.5-9B architecture.  Default workload c3 = BASELINE config 3 (1-hour video: F=3600, C=120 -> 90 000 image +
+36 000 audio + 32 text tokens = 126 032, "~128k"); the same fixed workload is used at every N (strong scaling):
+frames / chunks / tokens are sharded over ranks, the text stream is replicated, and the only data-path
+collective is the per-layer all-gather of the cross-attention (O, LSE) partials.
+Inputs are ~3.3 GB per step (> 126 MB L2) and every activation buffer is far larger than L2, so no explicit
+L2 flush is needed between steps (stated in config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (frames, chunks, text tokens, label)
+    "c3": (3600, 120, 32, "Vidi1.5-9B 1-hour synthetic video, 126k tokens (BASELINE config 3)"),
+    "c2p": (600, 20, 32, "Vidi1.5-9B 10-min synthetic video, 66k tokens (BASELINE config 2')"),
+    "c2": (80, 3, 32, "Vidi1.5-9B 80-frame synthetic video, 16.5k tokens (BASELINE config 2)"),
+    "c1": (8, 1, 32, "Vidi1.5-9B 8-frame plumbing case (BASELINE config 1)"),
+}
+METRIC = "prefill multimodal-tokens/sec, Vidi1.5-9B @128k seq"
+UNIT = "tokens/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def result(self):
+        s = sorted(self.samples)
+        return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    samples=len(s), **({"error": self.err} if self.err else {}))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# =====================================================================================================
+# reference arm / cpu_baseline: the fp32 oracle on the host cores, on a bounded sample, extrapolated
+# =====================================================================================================
+def cpu_sample(workload: str, budget_scale: float = 1.0):
+    """Times a bounded sample of the workload with the oracle (the reference has no CPU path and cannot be imported
+    here -- BASELINE.md section 4): a few tower / decoder layers at TRUE 9B dims on a few frames / tokens, scaled
+    linearly by layer, frame, chunk and token counts.  Returns (tokens_per_s, seconds_spent, description)."""
+    import dataclasses
+    from oracle import vidi15_ref as R                      # the one place bench.py executes oracle/ (cpu legs)
+    from vidi_b200 import synth
+    from vidi_b200.config import vidi15_9b, LLMCfg, VisionCfg, AudioCfg
+    torch.set_num_threads(os.cpu_count() or 1)
+    full = vidi15_9b()
+    F, Cn, T, _ = WORKLOADS[workload]
+    nf, vl, al, ll, ntok, nch = 12, 2, 1, 1, 6144, 6          # frames, vit layers, whisper layers, llm layers, tokens, chunk fraction
+    cfg = dataclasses.replace(full, llm=dataclasses.replace(LLMCfg(), layers=ll, vocab=1024),
+                              vis=dataclasses.replace(VisionCfg(), layers=vl + 1), aud=dataclasses.replace(AudioCfg(), layers=al))
+    sd = synth.make_state_dict(cfg, seed=1234)
+    t_all = time.time()
+    with torch.no_grad():
+        img = torch.randn(nf, 3, 384, 384).clamp_(-1, 1)
+        t0 = time.time(); R.siglip_tower(sd, cfg, img); t_vit = (time.time() - t0) / (nf * vl)          # s / frame / layer
+        # whisper layers on a quarter chunk (attention is quadratic in 1500; measure at full length for fidelity)
+        x = torch.randn(nch, 1500, cfg.aud.d_model)
+        p = "model.mm_aud.encoder.layers.0"
+        t0 = time.time()
+        h = R.layer_norm(x, sd[f"{p}.self_attn_layer_norm.weight"], sd[f"{p}.self_attn_layer_norm.bias"], 1e-5)
+        x = x + R._mha(h, sd, f"{p}.self_attn", cfg.aud.heads)
+        h = R.layer_norm(x, sd[f"{p}.final_layer_norm.weight"], sd[f"{p}.final_layer_norm.bias"], 1e-5)
+        x = x + R.linear(torch.nn.functional.gelu(R.linear(h, sd[f"{p}.fc1.weight"], sd[f"{p}.fc1.bias"])), sd[f"{p}.fc2.weight"], sd[f"{p}.fc2.bias"])
+        t_aud = (time.time() - t0) / nch                                                                  # s / chunk / layer
+        S = torch.randn(ntok, cfg.llm.hidden)
+        t0 = time.time(); S2, K, V = R.stream_layer(S, sd, "model.layers.0", cfg); t_llm = (time.time() - t0) / ntok   # s / token / layer
+        H = torch.randn(T, cfg.llm.hidden)
+        cos, sin = R.rope_cos_sin(T, cfg.llm.head_dim, cfg.llm.rope_theta)
+        t0 = time.time(); R.text_layer(H, sd, "model.layers.0", cfg, 0, cos, sin, [(K, V, torch.ones(ntok, dtype=torch.bool))])
+        t_txt = time.time() - t0                                                                          # s / layer at ntok keys
+    n_img, n_aud = full.image_tokens(F), full.audio_tokens(min(F * 100, Cn * 3000))
+    est = (F * full.vis.run_layers * t_vit + Cn * full.aud.layers * t_aud + (n_img + n_aud) * (full.llm.layers - 1) * t_llm
+           + full.llm.layers * t_txt * max(1.0, (n_img + n_aud) / ntok))
+    tokens = n_img + n_aud + T
+    desc = (f"fp32 oracle, {os.cpu_count()} threads: {vl} SigLIP layers x {nf} frames, 1 Whisper layer x {nch} chunks, 1 Dattn stream layer x "
+            f"{ntok} tokens, 1 text layer; scaled linearly to {F} frames x {full.vis.run_layers} layers, {Cn} chunks x "
+            f"{full.aud.layers} layers, {n_img + n_aud} tokens x {full.llm.layers - 1} layers (extrapolated)")
+    return tokens / est, time.time() - t_all, desc
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    vals, spent = [], 0.0
+    for i in range(args.warmup + args.steps):
+        v, s, desc = cpu_sample(args.workload)
+        spent += s
+        if i >= args.warmup:
+            vals.append(v)
+    val = sum(vals) / len(vals)
+    F, Cn, T, label = WORKLOADS[args.workload]
+    tokens = None
+    from vidi_b200.config import vidi15_9b
+    c = vidi15_9b()
+    tokens = c.image_tokens(F) + c.audio_tokens(min(F * 100, Cn * 3000)) + T
+    line = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=tokens / val * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=label, frames=F, audio_chunks=Cn, text_tokens=T, total_tokens=tokens),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count(), kind="port", sample=desc),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note="the reference has no CPU path and cannot be imported under this image's transformers (SURVEY.md 8c); "
+                     "this arm times the oracle port of its forward on the host cores, extrapolated from a bounded sample")
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def run_ours(args):
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    from vidi_b200 import ops, synth
+    from vidi_b200.config import vidi15_9b
+    from vidi_b200.engine import make_plan
+    from vidi_b200.model import DattnGemma2ForCausalLM
+
+    cfg = vidi15_9b()
+    F, Cn, T, label = WORKLOADS[args.workload]
+    t0 = time.time()
+    sd = synth.make_state_dict(cfg, seed=1234, device=dev, dtype=torch.bfloat16)
+    model = DattnGemma2ForCausalLM(cfg, sd, device=dev, rank=rank, world=world, group=group, pop_state_dict=True)
+    del sd
+    eng = model.engine
+    torch.cuda.synchronize()
+    t_load = time.time() - t0
+
+    # synthetic inputs: host copies are pinned bf16, the form ask() hands to generate()
+    g = torch.Generator(); g.manual_seed(4321)
+    asz = min(F * 100, Cn * 3000)
+    plan = make_plan(cfg, F, Cn, asz, rank, world)
+    ids = torch.randint(3, cfg.llm.vocab, (1, T + 1), generator=g); ids[0, 0] = 2; ids[0, 1] = -200
+    g_dev = torch.Generator(device=dev); g_dev.manual_seed(4321)
+    # every rank holds the full host tensors (as the reference replicates inputs inside an SP group); only its shard moves
+    host_img = torch.empty(1, F, 3, 384, 384, dtype=torch.bfloat16).pin_memory()
+    chunk = 256
+    for s in range(0, F, chunk):
+        e = min(F, s + chunk)
+        gi = torch.Generator(device=dev); gi.manual_seed(4321 + s)
+        host_img[0, s:e].copy_(torch.randn(e - s, 3, 384, 384, generator=gi, device=dev).clamp_(-1, 1).to(torch.bfloat16))
+    host_mel = (0.5 * torch.randn(1, Cn, 128, 3000, generator=g)).to(torch.bfloat16).pin_memory()
+    dev_img = host_img[0, plan.f0:plan.f1].to(dev)
+    dev_mel = host_mel[0, plan.c0:plan.c1].to(dev)
+    ids_dev = ids[0][ids[0] != -200].to(dev)
+    n_tokens = plan.n_img_total + plan.n_aud_total + T
+
+    def step_device():
+        return eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, logits_to_keep=0)
+
+    def step_e2e():
+        out = model.forward(ids, images=host_img, audios=host_mel, audio_sizes=[asz])
+        return out.logits[0, -1].float().cpu()                       # device->host read of the step's result
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        ops.reset_launch_count()
+        if profile:
+            ops.PROFILE = []
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        launches = ops.launch_count()
+        prof, ops.PROFILE = ops.PROFILE, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_device, args.steps, profile=True)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    # GEMM family roofline from the per-launch CUDA events recorded inside the timed region
+    by_tag = {}
+    for tag, fl, e0, e1 in prof:
+        d = by_tag.setdefault(tag, [0.0, 0.0, 0])
+        d[0] += fl; d[1] += e0.elapsed_time(e1); d[2] += 1
+    tot_fl = sum(v[0] for k, v in by_tag.items() if k != "text")
+    tot_ms = sum(v[1] for k, v in by_tag.items() if k != "text")
+    n_l = sum(v[2] for k, v in by_tag.items() if k != "text")
+    pk = peaks()
+    achieved = tot_fl / tot_ms / 1e9 if tot_ms > 0 else 0.0
+    roofline = dict(kernel="gemm_bf16_kernel (tcgen05/TMEM/TMA), all stream + tower launches in the timed region",
+                    bound="tensor", achieved=round(achieved, 1), peak=pk["tensor"], unit="TFLOP/s",
+                    frac=round(achieved / pk["tensor"], 4), peak_src=f"{pk['src']} bf16_tflops_sustained", traffic=None,
+                    launches=n_l, share_of_step=round(tot_ms / ms, 4),
+                    by_site={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms_per_step=round(v[1] / args.steps, 3), launches=v[2] // args.steps)
+                             for k, v in sorted(by_tag.items()) if v[1] > 0})
+    # end-to-end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    h2d = dev_img.numel() * 2 + dev_mel.numel() * 2 + ids.numel() * 8
+    d2h = cfg.llm.vocab * 4
+    if rank != 0:
+        return
+    value = n_tokens * args.steps / (ms / 1e3)
+    e2e_v = n_tokens * args.steps / (ms_e2e / 1e3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, spent, desc = cpu_sample(args.workload)
+        cpu = dict(value=round(v, 3), unit=UNIT, cores=os.cpu_count(), kind="port", sample=desc, seconds=round(spent, 1))
+    line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload=label, model="Vidi1.5-9B (Gemma2-9B Dattn + SigLIP-so400m/14@384 + Whisper-large-v3 enc), random init",
+                            frames=F, audio_chunks=Cn, text_tokens=T, image_tokens=plan.n_img_total, audio_tokens=plan.n_aud_total,
+                            total_tokens=n_tokens, parallelism=f"stream-shard x{world} (frames/chunks/tokens), text replicated",
+                            l2="inputs and activations >> 126 MB L2; no explicit flush"),
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=round(e2e_v, 1), unit=UNIT, ms_per_step=round(ms_e2e / args.steps, 2), h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors"),
+                gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,18 +4,21 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / `
 legs may import this module, and only as the checker / reported baseline.  The product path
 (``vidi_b200``) never imports it and fails loudly when its CUDA library is missing.
 
-PARITY PINNING: the reference (bytedance/vidi @ fc30c87) ships no tests, no golden vectors and no
-CPU path, and its model package cannot be imported here (transformers pins 4.50.0 vs 5.5.0
-installed; flash-attn / deepspeed hard requirements) -- SURVEY.md section 8(c).  What IS pinned:
-  * the reference-owned leaf modules that are plain torch (Conv2DPool, space_to_depth,
-    resize_by_tokens, LearnablePosEmbd, RMSNorm/rms_norm, MLP) are loaded from /root/reference by
-    file path in ``tests/golden/make_golden.py`` and their outputs are committed as fixtures that
-    ``tests/test_oracle_golden.py`` checks this restatement against;
-  * the third-party blocks the reference subclasses (HF SiglipVisionModel, WhisperEncoder,
-    Gemma2RMSNorm / Gemma2MLP / rotary / eager attention) are instantiated from the *installed*
-    transformers with the same weights and compared in the same fixture script.
-The Dattn decoder layer itself (gemma.py:125-244) has no runnable reference here: for that
-function this oracle is "parity unpinned" and follows the source line by line (citations below).
+PARITY PINNING: the reference (bytedance/vidi @ fc30c87) ships no tests and no golden vectors, has no
+CPU path, and does not import as-is under this image's transformers 5.5.0 (pins 4.50.0; flash-attn /
+deepspeed hard requirements) -- SURVEY.md section 8(c).  The oracle is nevertheless PINNED against
+outputs of the reference itself run here: ``tests/golden/make_golden.py`` imports the reference's
+unmodified modules from /root/reference through an import shim (``tests/golden/ref_shim.py``: absent
+packages stubbed, ``flash_attn_func`` replaced by an eager fp32 restatement of its semantics) and
+commits the outputs of
+  * Conv2DPool / space_to_depth / resize_by_tokens / LearnablePosEmbd / RMSNorm / rms_norm / MLP,
+  * DattnMMMixin.encode_video_images / encode_video_audios (on HF SiglipVisionModel / WhisperEncoder),
+  * DattnGemma2DecoderLayer.forward + forward_xattn + flash_cross_attention_forward + splitted_call
+    (two stacked layers, all three streams; the T2T half runs the installed HF Gemma2Attention),
+which ``tests/test_oracle_golden.py`` checks this restatement against to <= 5e-5.
+Not pinned (no runnable reference): the model-level loop DattnGemma2Model.forward (gemma.py:267-424:
+normaliser, layer loop, final norm) and lm_head + soft-cap (gemma.py:564-569) -- HF 5.x removed the
+cache classes that loop constructs; those ~10 lines are restated from the source (citations below).
 
 Everything is fp32; functions take an HF-layout ``state_dict`` (keys of SURVEY.md section 8b).
 """

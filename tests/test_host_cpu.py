@@ -1,0 +1,112 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host-side shard/token logic,
+weight repacking algebra, and the facade's error behaviour.  No kernel is launched here."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from vidi_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "vidi_b200.h")).read()
+    declared = set(re.findall(r"\b(vidi_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/vidi_b200.h but not exported"
+    assert declared == set(lib.SIGNATURES) | set(lib.EXTRA_SYMBOLS)
+    assert L.vidi_abi_version() == 1
+    assert isinstance(L.vidi_launch_count(), int)
+
+
+def test_ops_refuse_cpu_tensors():
+    from vidi_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_engine_fails_loudly_without_gpu():
+    from vidi_b200.config import vidi15_mini
+    from vidi_b200.engine import Vidi15Engine
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Vidi15Engine(vidi15_mini(), {}, device="cuda")
+
+
+def test_token_math_follows_reference():
+    """multimodal.py:175-180 + utils.py:152-171: 196 tokens/frame up to 306 frames, then shrink, floor 10x10."""
+    from vidi_b200.config import vidi15_9b
+    c = vidi15_9b()
+    assert c.image_tokens(8) == 1568 and c.image_tokens(80) == 15680 and c.image_tokens(306) == 306 * 196
+    assert c.image_hw(307) != (28, 28)
+    assert c.image_tokens(600) == 60000 and c.image_tokens(3600) == 90000 and c.image_tokens(1800) == 45000
+    assert c.audio_tokens(800) == 80 and c.audio_tokens(360000) == 36000 and c.audio_tokens(1234) == 123
+    assert c.vis.run_layers == 26 and c.vis.patches == 729
+
+
+@pytest.mark.parametrize("F,C,asz,world", [(3600, 120, 360000, 8), (80, 3, 8000, 2), (5, 3, 7000, 3), (7, 1, 500, 4), (600, 20, 60000, 8)])
+def test_shard_plan_partitions_exactly(F, C, asz, world):
+    from vidi_b200.config import vidi15_9b
+    from vidi_b200.engine import make_plan
+    cfg = vidi15_9b()
+    plans = [make_plan(cfg, F, C, asz, r, world) for r in range(world)]
+    assert plans[0].f0 == 0 and plans[-1].f1 == F and plans[0].c0 == 0 and plans[-1].c1 == C
+    for a, b in zip(plans, plans[1:]):
+        assert a.f1 == b.f0 and a.c1 == b.c0 and a.a1 == b.a0
+    assert sum(p.n_img for p in plans) == cfg.image_tokens(F) == plans[0].n_img_total
+    assert sum(p.n_aud for p in plans) == cfg.audio_tokens(asz) == plans[0].n_aud_total
+    assert max(p.f1 - p.f0 for p in plans) - min(p.f1 - p.f0 for p in plans) <= 1
+    for p in plans:                                   # every audio token of a rank comes from that rank's chunks
+        assert p.c0 * p.tpc <= p.a0 or p.n_aud == 0
+        assert p.a1 <= p.c1 * p.tpc
+
+
+def test_fold_o_proj_equals_repeat_kv_then_project():
+    """K13: o_proj(repeat_kv(V)) == V @ W_o'^T with W_o' = sum over the group axis (gemma.py:77-78,195-197)."""
+    from vidi_b200.weights import fold_o_proj
+    D, Hkv, G, dh, N = 48, 2, 3, 8, 11
+    Wo = torch.randn(D, Hkv * G * dh, dtype=torch.float64)
+    V = torch.randn(N, Hkv * dh, dtype=torch.float64)
+    Vrep = V.view(N, Hkv, dh).repeat_interleave(G, 1).reshape(N, -1)
+    ref = Vrep @ Wo.t()
+    out = V @ fold_o_proj(Wo, Hkv, G, dh).double().t()
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_pack_glu_layout():
+    from vidi_b200.weights import pack_glu
+    I, K, bn = 512, 16, 256
+    wg = torch.arange(I * K, dtype=torch.float32).view(I, K); wu = -wg
+    p = pack_glu(wg, wu, bn)
+    h = bn // 2
+    for t in range(I // h):
+        assert torch.equal(p[t * bn:t * bn + h], wg[t * h:(t + 1) * h])
+        assert torch.equal(p[t * bn + h:(t + 1) * bn], wu[t * h:(t + 1) * h])
+
+
+def test_projector_column_permutation_matches_pool_kernel_order():
+    """weights.py permutes W1 columns from the reference's c*m*m+q order (utils.py:143-150) to the pool kernel's q*d+c."""
+    from oracle import vidi15_ref as R
+    d, m = 6, 2
+    x = torch.randn(1, d, 4, 4)
+    ref_order = R.space_to_depth(x, m).permute(0, 2, 3, 1)                       # [...,(c, q)]
+    ker_order = ref_order.reshape(1, 2, 2, d, m * m).permute(0, 1, 2, 4, 3).reshape(1, 2, 2, m * m * d)
+    W = torch.randn(5, d * m * m)
+    Wp = W.reshape(5, d, m * m).permute(0, 2, 1).reshape(5, m * m * d)
+    assert torch.allclose(ref_order @ W.t(), ker_order @ Wp.t(), atol=1e-5)
+
+
+def test_facade_errors_and_sentinel_handling():
+    from vidi_b200.model import DattnGemma2ForCausalLM, IMAGE_TOKEN_INDEX, config_from_hf_json
+    ids = torch.tensor([2, IMAGE_TOKEN_INDEX, 5, 6, 7])
+    assert DattnGemma2ForCausalLM._strip(ids, None).tolist() == [2, 5, 6, 7]
+    assert DattnGemma2ForCausalLM._strip(ids, torch.tensor([1, 1, 1, 0, 1])).tolist() == [2, 5, 7]
+    with pytest.raises(AssertionError, match="at most one image"):
+        DattnGemma2ForCausalLM._strip(torch.tensor([IMAGE_TOKEN_INDEX, IMAGE_TOKEN_INDEX, 3]), None)
+    cfg = config_from_hf_json({"hidden_size": 3584, "mm_image_pool_size": 2, "mm_audio_pool_size": 5})
+    assert cfg.llm.layers == 42 and cfg.llm.kv_dim == 2048 and cfg.mm_time_interval == 10000

@@ -1,0 +1,99 @@
+"""Pins the oracle (oracle/vidi15_ref.py) against fixtures produced by running the REFERENCE'S OWN modules and the HF
+blocks it subclasses (tests/golden/make_golden.py, generated in the build container where /root/reference exists)."""
+import os
+
+import pytest
+import torch
+
+from oracle import vidi15_ref as R
+from vidi_b200 import synth
+from vidi_b200.config import AudioCfg, LLMCfg, Vidi15Config, VisionCfg
+
+G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vidi15_reference_golden.pt"), weights_only=False)
+
+
+def close(a, b, tol=2e-5):
+    a, b = a.float(), b.float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max())
+    assert err <= tol * max(1.0, float(b.abs().max())), err
+
+
+def tiny_cfg():
+    c = G["cfg"]
+    return Vidi15Config(llm=LLMCfg(**c["llm"]), vis=VisionCfg(**c["vis"]), aud=AudioCfg(**c["aud"]), name="golden-tiny")
+
+
+def test_conv2dpool_and_space_to_depth_match_reference():
+    for key, ref in G["pool"]["out"].items():
+        h, w = map(int, key.split("x"))
+        close(R.conv2d_pool(G["pool"]["x"], (h, w), 2), ref, 1e-6)
+    close(R.space_to_depth(G["s2d"]["x"], 2), G["s2d"]["out"], 0)
+
+
+def test_resize_by_tokens_matches_reference():
+    cfg = Vidi15Config()
+    for B, hw in G["resize_by_tokens"].items():
+        side = cfg.vis.side + 1
+        if B * side * side > cfg.max_image_tokens * 4:
+            assert cfg.image_hw(B) == tuple(hw), (B, cfg.image_hw(B), hw)
+    assert cfg.image_hw(306) == (28, 28) and cfg.image_hw(3600) == (10, 10) and cfg.image_hw(600) == (20, 20)
+
+
+def test_pos_embed_norm_mlp_match_reference():
+    p = G["pos"]
+    sd = {f"h.{k}": v for k, v in p["h_sd"].items()} | {f"t.{k}": v for k, v in p["t_sd"].items()}
+    close(R.pos_embed(sd, "h", 14, 2, 32), p["h_out"])
+    close(R.pos_embed(sd, "t", 37, 10000, 32), p["t_out"], 2e-4)     # sin/cos of arguments up to 1e4 rad
+    n = G["norm"]
+    close(R.mm_norm(n["x"], n["w"], 1e-5), n["out"], 1e-6)
+    close(R.xhat(n["x"], 1e-5), n["out_plain"], 1e-6)
+    m = G["mlp"]
+    close(R.projector({f"p.{k}": v for k, v in m["sd"].items()}, "p", m["x"]), m["out"], 1e-6)
+
+
+def test_towers_match_installed_hf_blocks():
+    cfg = tiny_cfg()
+    sd = synth.make_state_dict(cfg, seed=G["seed"])
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=99, audio_size=1234)
+    close(R.siglip_tower(sd, cfg, images), G["siglip"]["hidden_m2"], 2e-5)
+    close(R.whisper_encoder(sd, cfg, mels), G["whisper"]["out"], 2e-5)
+
+
+def test_encode_video_matches_reference_mixin():
+    cfg = tiny_cfg()
+    sd = synth.make_state_dict(cfg, seed=G["seed"])
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=99, audio_size=1234)
+    e = G["encode"]
+    X, mX = R.encode_video_images(sd, cfg, images)
+    A, mA = R.encode_video_audios(sd, cfg, mels, asz)
+    close(X, e["image_embeds"], 5e-5); close(A, e["audio_embeds"], 5e-5)
+    assert torch.equal(mX, e["image_mask"].bool()) and torch.equal(mA, e["audio_mask"].bool())
+    assert X.shape[0] == cfg.image_tokens(3) and A.shape[0] == cfg.audio_tokens(asz)
+
+
+def test_decoder_layers_match_reference_layer_forward():
+    cfg = tiny_cfg()
+    sd = synth.make_state_dict(cfg, seed=G["seed"])
+    d = G["decoder"]
+    H, S_img, S_aud = d["H0"], d["img0"], d["aud0"]
+    T = H.shape[0]
+    cos, sin = R.rope_cos_sin(T, cfg.llm.head_dim, cfg.llm.rope_theta)
+    ones_i, ones_a = torch.ones(S_img.shape[0], dtype=torch.bool), torch.ones(S_aud.shape[0], dtype=torch.bool)
+    for l, ref in enumerate(d["layers"]):
+        p = f"model.layers.{l}"
+        S_img2, Ki, Vi = R.stream_layer(S_img, sd, p, cfg)
+        S_aud2, Ka, Va = R.stream_layer(S_aud, sd, p, cfg)
+        H = R.text_layer(H, sd, p, cfg, l, cos, sin, [(Ki, Vi, ones_i), (Ka, Va, ones_a)])
+        S_img, S_aud = S_img2, S_aud2
+        close(S_img, ref["image"], 5e-5); close(S_aud, ref["audio"], 5e-5); close(H, ref["text"], 5e-5)
+
+
+def test_prefill_consistency_with_layer_fixture():
+    """The oracle's own prefill() must reproduce the layer-by-layer path that was pinned above."""
+    cfg = tiny_cfg()
+    sd = synth.make_state_dict(cfg, seed=G["seed"])
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=99, audio_size=1234)
+    logits, inter = R.prefill(sd, cfg, ids, images, mels, asz, return_intermediates=True)
+    close(inter["text_hidden"][-1], G["decoder"]["layers"][-1]["text"], 5e-5)
+    assert logits.shape == (6, cfg.llm.vocab) and float(logits.abs().max()) <= 30.0

@@ -95,12 +95,12 @@ class Vidi15Engine:
     # ------------------------------------------------------------------------------------------
     def _tower_layer(self, x, L, B, S, heads, dh, eps, act):
         h = ops.layernorm(x, L.ln1_w, L.ln1_b, eps)
-        qkv = ops.gemm(h, L.wqkv, bias=L.bqkv)
+        qkv = ops.gemm(h, L.wqkv, bias=L.bqkv, tag="tower")
         a = ops.attn_dense(qkv, B, S, heads, dh, dh ** -0.5)
-        ops.gemm(a, L.wo, bias=L.bo, residual=x, out=x)
+        ops.gemm(a, L.wo, bias=L.bo, residual=x, out=x, tag="tower")
         h = ops.layernorm(x, L.ln2_w, L.ln2_b, eps, out=h)
-        m = ops.gemm(h, L.w1, bias=L.b1, act=act)
-        ops.gemm(m, L.w2, bias=L.b2, residual=x, out=x)
+        m = ops.gemm(h, L.w1, bias=L.b1, act=act, tag="tower")
+        ops.gemm(m, L.w2, bias=L.b2, residual=x, out=x, tag="tower")
         return x
 
     def siglip(self, images: torch.Tensor) -> torch.Tensor:
@@ -108,7 +108,7 @@ class Vidi15Engine:
         v, Wv = self.cfg.vis, self.W.vis
         f = images.shape[0]
         A = ops.patch_im2col(images, v.patch, Wv.kpad)
-        x = ops.gemm(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches)
+        x = ops.gemm(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches, tag="vit", alg_k=3 * v.patch * v.patch)
         del A
         for L in Wv.layers:
             x = self._tower_layer(x, L, f, v.patches, v.heads, v.head_dim, v.eps, ops.ACT_GELU_TANH)
@@ -136,8 +136,8 @@ class Vidi15Engine:
         if rows == 0:
             return torch.zeros(1, D, device=self.device)
         A = ops.sinusoid_split(self.W.div_term, rows, i0, l, N, D)
-        h = ops.gemm(A, P.w0, bias=P.b0, act=ops.ACT_GELU_ERF, out_fp32=True)
-        y = ops.gemm(ops.split3(h, 0), P.w2, bias=P.b2, out_fp32=True)
+        h = ops.gemm(A, P.w0, bias=P.b0, act=ops.ACT_GELU_ERF, out_fp32=True, tag="pos", alg_k=D)
+        y = ops.gemm(ops.split3(h, 0), P.w2, bias=P.b2, out_fp32=True, tag="pos", alg_k=D)
         return ops.rmsnorm_f32(y, self.cfg.mm_eps, round_bf16=True)
 
     def _project(self, x, proj):
@@ -207,13 +207,13 @@ class Vidi15Engine:
         y = torch.empty_like(S)
         g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
-            ops.gemm(h, L.wkv, out=kv[l])
+            ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv")
             if l == len(Ls) - 1:
                 break
-            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y)
+            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo")
             ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
-            ops.gemm(h, L.wgu, glu=ops.GLU_GELU_TANH, out=g)
-            ops.gemm(g, L.wd, out=y)
+            ops.gemm(h, L.wgu, glu=ops.GLU_GELU_TANH, out=g, tag="llm_gateup")
+            ops.gemm(g, L.wd, out=y, tag="llm_down")
             ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
         return kv
 
@@ -250,7 +250,7 @@ class Vidi15Engine:
         att = torch.empty(Tq, qd, device=self.device, dtype=torch.float32)
         y = torch.empty(Tq, c.hidden, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
-            qkv = ops.gemm(h, L.wqkv)
+            qkv = ops.gemm(h, L.wqkv, tag="text")
             if text_cache is not None:
                 tkv = text_cache["kv"][l]
                 tkv[pos0:pos0 + Tq].copy_(qkv[:, qd:])
@@ -281,17 +281,17 @@ class Vidi15Engine:
                                 rank_stride_l=flat.numel(), rows=rows, dh=dh)
                 off += sz
             a = ops.cast_bf16(att)
-            ops.gemm(a, L.wo, out=y)
+            ops.gemm(a, L.wo, out=y, tag="text")
             h2 = torch.empty_like(H)
             ops.residual_norm(H, y, L.n_post, L.n_preff, h2, c.rms_eps, 1, True)
-            g = ops.gemm(h2, L.wgu, glu=ops.GLU_GELU_TANH)
-            ops.gemm(g, L.wd, out=y)
+            g = ops.gemm(h2, L.wgu, glu=ops.GLU_GELU_TANH, tag="text")
+            ops.gemm(g, L.wd, out=y, tag="text")
             w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else self.W.final_norm
             ops.residual_norm(H, y, L.n_postff, w_next, h, c.rms_eps, 1, True)
         if text_cache is not None:
             text_cache["len"] = pos0 + Tq
         hn = h if not logits_to_keep else h[-logits_to_keep:]
-        return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True)
+        return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True, tag="text")
 
     # ------------------------------------------------------------------------------------------
     # whole prefill for one sample
