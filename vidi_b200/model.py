@@ -106,6 +106,14 @@ class DattnGemma2ForCausalLM:
             return None
         return t.to(device=self.device, dtype=BF16, non_blocking=True).contiguous()
 
+    def _any_nonzero(self, shard: torch.Tensor) -> bool:
+        """`sum(abs(x)) != 0` over the whole sample (multimodal.py:202,246), evaluated on the uploaded shard and
+        OR-ed over ranks.  One tiny device reduction + one host read per modality per forward."""
+        flag = shard.any().to(torch.int32) if shard.numel() else torch.zeros((), device=self.device, dtype=torch.int32)
+        if self.engine.world > 1:
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=self.engine.group)
+        return bool(flag.item())
+
     @staticmethod
     def _strip(ids_row: torch.Tensor, mask_row: Optional[torch.Tensor]) -> torch.Tensor:
         if mask_row is not None:
@@ -121,14 +129,14 @@ class DattnGemma2ForCausalLM:
         iv = av = True
         if images is not None:
             F = images.shape[0]
-            iv = bool(images.abs().sum() != 0)                           # multimodal.py:202 (input validity, not compute)
             plan = make_plan(self.cfg, F, audios.shape[0] if audios is not None else 0, audio_size or 0, eng.rank, eng.world)
             img = self._dev(images[plan.f0:plan.f1])
+            iv = self._any_nonzero(img)                                  # multimodal.py:202 (input validity, not compute)
         if audios is not None:
             Cn = audios.shape[0]
-            av = bool(audios.abs().sum() != 0)
             plan = make_plan(self.cfg, F, Cn, audio_size or 0, eng.rank, eng.world)
             aud = self._dev(audios[plan.c0:plan.c1])
+            av = self._any_nonzero(aud)
         tc = eng.new_text_cache(max_len)
         ids_dev = ids.to(self.device, dtype=torch.int64).contiguous()
         logits, st = eng.prefill(ids_dev, img, aud, audio_size or 0, n_frames_total=F, n_chunks_total=Cn,
