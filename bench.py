@@ -247,7 +247,7 @@ def run_ours(args):
             ms = float(t)
         return ms, launches, prof
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(1 if args.quick else max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -273,9 +273,12 @@ def run_ours(args):
                     by_site={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms_per_step=round(v[1] / args.steps, 3), launches=v[2] // args.steps)
                              for k, v in sorted(by_tag.items()) if v[1] > 0})
     # end-to-end through the public API with host buffers
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if args.quick:
+        ms_e2e = ms
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _, _ = timed(step_e2e, args.steps)
     h2d = dev_img.numel() * 2 + dev_mel.numel() * 2 + ids.numel() * 8
     d2h = cfg.llm.vocab * 4
     if rank != 0:
@@ -283,7 +286,7 @@ def run_ours(args):
     value = n_tokens * args.steps / (ms / 1e3)
     e2e_v = n_tokens * args.steps / (ms_e2e / 1e3)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
         v, spent, desc = cpu_sample(args.workload)
         cpu = dict(value=round(v, 3), unit=UNIT, cores=os.cpu_count(), kind="port", sample=desc, seconds=round(spent, 1))
     line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -308,6 +311,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="1 warm-up, no e2e / cpu legs (for ncu launch lists; not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -67,6 +67,10 @@ int vidi_whisper_im2col1(const void* mel, void* out, int C, int mels, int T, voi
 int vidi_whisper_im2col2(const void* x, void* out, int C, int T, int d, void* stream);                     /* K8 conv2 */
 /* Conv2DPool: pad + bilinear + space_to_depth gather (mm_vision/pool.py:23-32, utils.py:134-150), K4 */
 int vidi_pool_s2d(const void* P, void* X, int F, int side, int d, int h, int w, int m, void* stream);
+/* Vidi-7B learned pool (Vidi_7B/model/mm_vision/pool.py:6-26): k x k stride-1 window gather feeding the conv GEMM, and the
+ * bilinear(align_corners=True) resize of the token-major map [F,si,si,d] -> [F,so,so,d] */
+int vidi_conv_window_gather(const void* P, void* A, int F, int side, int d, int k, void* stream);
+int vidi_bilinear_ac(const void* X, void* Y, int F, int si, int so, int d, void* stream);
 int vidi_embed_gather(const int64_t* ids, const void* E, void* out, int T, int D, int vocab, float normalizer, void* stream);
 int vidi_sinusoid_split(const float* div_term, void* out, int rows, int i0, int l, int N, int D, void* stream); /* pos.py:18-26,48-56 */
 int vidi_split3(const float* x, void* out, int64_t rows, int D, int mode, void* stream);
@@ -76,11 +80,18 @@ int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 /* bidirectional flash attention for the towers (flash_attn_func via HF SiglipAttention / WhisperAttention), K3/K8 */
 int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,
                     int dh, float scale, void* stream);
+/* same contract, always the warp-level mma.sync kernel (generic strides / head dims; kept as the A/B bar for the tcgen05 path) */
+int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
+                        int H, int dh, float scale, void* stream);
 /* split-KV cross attention, replaces flash_cross_attention_forward (lmm/dattn/xattn.py:141-263) as called from
  * DattnGemma2Attention.forward_xattn (gemma.py:81-91).  Opart fp32 [splits,T,Hq,dh], LSE fp32 [splits,T,Hq]. */
 int vidi_xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
                        int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
                        void* stream);
+/* same contract, always the warp-level mma.sync kernel (any head dim in {128,256}, soft-cap optional: the Vidi-7B path) */
+int vidi_xattn_splitkv_mma(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
+                           int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
+                           void* stream);
 /* LSE merge of P partials into fp32 out [rows, dh] (replaces the reference's all-gather of full K/V: all_to_all.py:361).
  * partial p = (rank p / splits_per_rank, split p % splits_per_rank) is at Opart + rank*rank_stride_o + split*rows*dh and
  * LSE + rank*rank_stride_l + split*rows (strides in floats): the all-gathered per-rank [O | LSE] blocks merge in place. */

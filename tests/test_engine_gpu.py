@@ -116,3 +116,31 @@ def test_sharded_equals_single_rank_fake_multirank():
     seg_full = [(0, img_rows.shape[1], None, 1.0, img_rows.shape[1]), (img_rows.shape[1], aud_rows.shape[1], None, 1.0, aud_rows.shape[1])]
     logits2 = eng.text_pass(ids_dev, merged.contiguous(), seg_full)
     assert rel(logits2, full) < 1e-2
+
+
+def test_vidi7b_prefill_mini():
+    """Vidi-7B (Mistral Dattn): learned-conv pooling, SwiGLU, no post-norms / soft-caps, dh=128."""
+    from oracle import synth, vidi7b_ref as R7
+    from oracle.vidi15_ref import strip_image_token
+    from vidi_b200.config import vidi7b_mini
+    from vidi_b200.engine import Vidi15Engine
+    cfg = vidi7b_mini()
+    sd = synth.make_state_dict(cfg, seed=4242)
+    sd = {k: (v if "mm_rand_pos" in k else v.to(BF).float()) for k, v in sd.items()}
+    eng = Vidi15Engine(cfg, {k: v.clone() for k, v in sd.items()}, device="cuda")
+    assert not eng.gemma and eng.normalizer == 1.0
+    ids, images, mels, asz = synth.make_inputs(cfg, 5, 2, n_text=19, audio_size=4100)
+    images = images.to(BF).float(); mels = mels.to(BF).float()
+    ref, inter = R7.prefill(sd, cfg, ids, images, mels, asz, return_intermediates=True)
+    logits, st = eng.prefill(strip_image_token(ids).cuda(), images.cuda().to(BF), mels.cuda().to(BF), asz, return_state=True)
+    torch.cuda.synchronize()
+    n_img = inter["image_embeds"].shape[0]
+    assert n_img == 5 * cfg.mm_image_pool_size ** 2 and st["streams"].shape[0] == n_img + inter["audio_embeds"].shape[0]
+    kd = cfg.llm.kv_dim
+    K0 = torch.cat([inter["kv"][0][0][0], inter["kv"][0][1][0]], 0)
+    assert rel(st["kv"][0][:, :kd], K0) < 2e-2
+    err = float((logits.cpu() - ref).abs().max())
+    assert rel(logits, ref) < 3e-2 and err < 0.25, (rel(logits, ref), err)
+    top2 = ref.topk(2, -1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert torch.equal(logits.cpu().argmax(-1)[confident], ref.argmax(-1)[confident])

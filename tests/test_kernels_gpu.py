@@ -29,7 +29,7 @@ def rel_err(a, b):
     (128, 256, 64, 256), (128, 64, 64, 64), (256, 128, 128, 128),
     (300, 520, 288, 256), (300, 520, 288, 128), (77, 72, 1152, 64),
     (1000, 1152, 640, 256), (2048, 4096, 3584, 256), (4096, 3584, 2048, 128),
-    (33, 1024, 512, 256), (5000, 4304, 1152, 256),
+    (33, 1024, 512, 256), (5000, 4304, 1152, 256), (1000, 1152, 1152, 192), (300, 3456, 288, 192), (129, 384, 72, 192),
 ])
 def test_gemm_plain(M, N, K, bn):
     from vidi_b200 import ops
@@ -169,6 +169,24 @@ def test_pool_s2d(hw):
     assert rel_err(X.cpu(), ref) < 5e-3
 
 
+@pytest.mark.parametrize("s_out", [16, 4, 9])
+def test_vidi7b_conv_pool(s_out):
+    """Vidi-7B Conv2DPool: window gather + GEMM + bilinear(align_corners=True) vs the oracle (pool.py:6-26)."""
+    import math
+    from vidi_b200 import ops
+    from oracle import vidi7b_ref as R7
+    Fr, side, d = 2, 27, 64
+    k = math.ceil(side / s_out)
+    P = rnd(Fr, side * side, d, seed=40).to(BF)
+    w = rnd(d, d, k, k, scale=0.05, seed=41).to(BF)
+    A = ops.conv_window_gather(P, Fr, side, k)
+    Y = ops.gemm(A, w.permute(0, 2, 3, 1).reshape(d, -1).contiguous())
+    X = ops.bilinear_ac(Y, Fr, side - k + 1, s_out)
+    feats = P.float().cpu().reshape(Fr, side, side, d).permute(0, 3, 1, 2)
+    ref = R7.conv2d_pool_7b(feats, w.float().cpu(), s_out).permute(0, 2, 3, 1).reshape(-1, d)
+    assert rel_err(X.cpu(), ref) < 8e-3
+
+
 def test_whisper_im2col():
     from vidi_b200 import ops
     Cn, mels, T, d = 2, 128, 3000, 64
@@ -207,29 +225,33 @@ def test_embed_gather_and_pos_split():
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (1, 100, 2, 72), (2, 64, 2, 64)])
-def test_attn_dense(B, S, H, dh):
+@pytest.mark.parametrize("impl", ["auto", "mma"])
+@pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (1, 100, 2, 72), (2, 64, 2, 64), (5, 729, 16, 72),
+                                      (1, 129, 1, 72), (3, 257, 3, 64)])
+def test_attn_dense(B, S, H, dh, impl):
     from vidi_b200 import ops
     d = H * dh
     qkv = rnd(B * S, 3 * d, seed=36).to(BF)
-    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5)
+    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, impl=impl)
     q, k, v = [t.float().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1)]
     ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, d)
     assert rel_err(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("impl", ["auto", "mma"])
 @pytest.mark.parametrize("T,N,Hq,Hkv,dh,cap,splits", [
     (32, 5000, 16, 8, 256, 50.0, 7), (12, 300, 4, 2, 256, 50.0, 3), (40, 2048, 32, 8, 128, 0.0, 4),
-    (33, 1000, 16, 8, 256, 50.0, 1), (5, 31, 4, 2, 256, 50.0, 2),
+    (33, 1000, 16, 8, 256, 50.0, 1), (5, 31, 4, 2, 256, 50.0, 2), (64, 4097, 16, 8, 256, 50.0, 5), (70, 700, 16, 8, 256, 50.0, 3),
+    (32, 126000, 16, 8, 256, 50.0, 37),
 ])
-def test_xattn_splitkv_and_merge(T, N, Hq, Hkv, dh, cap, splits):
+def test_xattn_splitkv_and_merge(T, N, Hq, Hkv, dh, cap, splits, impl):
     from vidi_b200 import ops
     q = rnd(T, Hq * dh, seed=37).to(BF)
     kv = rnd(N, 2 * Hkv * dh, seed=38).to(BF)
     k, v = kv[:, :Hkv * dh], kv[:, Hkv * dh:]
     mask = torch.ones(N, device="cuda", dtype=torch.uint8); mask[N // 3: N // 3 + 5] = 0
     scale = dh ** -0.5
-    op, lse = ops.xattn_splitkv(q, k, v, mask, Hq, Hkv, dh, scale, cap, splits)
+    op, lse = ops.xattn_splitkv(q, k, v, mask, Hq, Hkv, dh, scale, cap, splits, impl=impl)
     out = torch.zeros(T * Hq, dh, device="cuda")
     ops.xattn_merge(op, lse, out)
     qh = q.float().view(T, Hq, dh).transpose(0, 1)

@@ -56,7 +56,9 @@ def dense_case(B, S, H, dh):
     out = torch.empty(B * S, d, device="cuda", dtype=BF)
     t = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out))
     fl = 4.0 * B * H * S * S * dh
-    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1))
+    t_m = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="mma"))
+    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), mma_ms=round(t_m, 4),
+               mma_tflops=round(fl / t_m / 1e9, 1))
     try:
         from flash_attn import flash_attn_func
         q, k, v = [x.reshape(B, S, H, dh) for x in qkv.split(d, 1)]
@@ -75,7 +77,7 @@ def rownorm_case(rows, D):
     print(json.dumps(dict(kernel="residual_norm", rows=rows, D=D, ms=round(t, 4), gbs=round(rows * D * 2 * 4 / t / 1e6, 1))), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[1] == "one"):
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "gemm"):
         M = 15750
@@ -92,8 +94,48 @@ if __name__ == "__main__":
         gemm_case("text_down", 32, 3584, 14336)
         gemm_case("text_down_bn64", 32, 3584, 14336, bn=64)
     if which in ("all", "attn"):
-        xattn_case(32, 126000)
+        for sp in (18, 37, 55, 74):
+            xattn_case(32, 126000, sp)
         xattn_case(32, 16000)
+        xattn_case(32, 15750, 18)
         dense_case(64, 729, 16, 72)
         dense_case(16, 1500, 20, 64)
         rownorm_case(126000, 3584)
+
+
+def one(name):
+    """`python tools/bench_kernels.py one <case>`: a few plain launches of one kernel, for ncu captures."""
+    cases = {
+        "gate_up": lambda: gemm_launcher(15750, 28672, 3584, 1),
+        "kv_proj": lambda: gemm_launcher(15750, 4096, 3584, 0),
+        "vit_fc2": lambda: gemm_launcher(46656, 1152, 4304, 0),
+        "vit_qkv": lambda: gemm_launcher(46656, 3456, 1152, 0),
+    }
+    if name in cases:
+        fn = cases[name]()
+    elif name == "attn_vit":
+        qkv = torch.randn(64 * 729, 3 * 1152, device="cuda").to(BF); out = torch.empty(64 * 729, 1152, device="cuda", dtype=BF)
+        fn = lambda: ops.attn_dense(qkv, 64, 729, 16, 72, 72 ** -0.5, out=out)
+    elif name == "xattn":
+        q = torch.randn(32, 4096, device="cuda").to(BF); kv = torch.randn(126000, 4096, device="cuda").to(BF)
+        op = torch.empty(37, 32, 16, 256, device="cuda"); ls = torch.empty(37, 32, 16, device="cuda")
+        fn = lambda: ops.xattn_splitkv(q, kv[:, :2048], kv[:, 2048:], None, 16, 8, 256, 1 / 16, 50.0, 37, opart=op, lse=ls)
+    elif name == "residual_norm":
+        x = torch.randn(126000, 3584, device="cuda").to(BF); y = torch.randn(126000, 3584, device="cuda").to(BF)
+        w = torch.randn(3584, device="cuda").to(BF); h = torch.empty_like(x)
+        fn = lambda: ops.residual_norm(x, y, w, w, h, 1e-6, 1, True)
+    else:
+        raise SystemExit(f"unknown case {name}")
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+
+
+def gemm_launcher(M, N, K, glu):
+    a = torch.randn(M, K, device="cuda").to(BF); w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
+    out = torch.empty(M, N // 2 if glu else N, device="cuda", dtype=BF)
+    return lambda: ops.gemm(a, w, out=out, glu=glu)
+
+
+if len(sys.argv) > 2 and sys.argv[1] == "one":
+    one(sys.argv[2])

@@ -512,14 +512,23 @@ static int launch_xattn(const void* Q, int64_t ldq, const void* K, const void* V
     return 0;
 }
 
+int xattn_splitkv_sm100(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int,
+                        float, float, float*, float*, cudaStream_t);
+
 int xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T, int N,
-                  int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
+                  int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE, int force_mma,
                   cudaStream_t st) {
     VB_REQUIRE(T > 0 && N >= 0 && splits > 0 && Hq % Hkv == 0, "xattn_splitkv: bad shape T=%d N=%d splits=%d", T, N, splits);
     VB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "xattn_splitkv: alignment");
     int kps = (N + splits - 1) / splits;
-    kps = ((kps + 31) / 32) * 32;
-    if (kps == 0) kps = 32;
+    kps = ((kps + 63) / 64) * 64;
+    if (kps == 0) kps = 64;
+    // soft-capped dh=256 (Gemma2) -> tcgen05/TMEM/TMA streaming kernel; otherwise the warp-level mma.sync kernel
+    const int G = Hq / Hkv;
+    if (!force_mma && dh == 256 && softcap > 0.f && softcap * kLog2e <= 80.f && 128 % G == 0 &&
+        (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (kmask == nullptr || (reinterpret_cast<uintptr_t>(kmask) & 15) == 0))
+        return xattn_splitkv_sm100(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
     if (dh == 256) return launch_xattn<256>(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
     if (dh == 128) return launch_xattn<128>(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
     VB_REQUIRE(false, "xattn_splitkv: unsupported head_dim %d (have 128, 256)", dh);

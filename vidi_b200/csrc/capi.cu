@@ -20,13 +20,16 @@ int patch_im2col(const void*, void*, int, int, int, int, cudaStream_t);
 int whisper_im2col1(const void*, void*, int, int, int, cudaStream_t);
 int whisper_im2col2(const void*, void*, int, int, int, cudaStream_t);
 int pool_s2d(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int conv_window_gather(const void*, void*, int, int, int, int, cudaStream_t);
+int bilinear_ac(const void*, void*, int, int, int, int, cudaStream_t);
 int embed_gather(const int64_t*, const void*, void*, int, int, int, float, cudaStream_t);
 int sinusoid_split(const float*, void*, int, int, int, int, int, cudaStream_t);
 int split3(const float*, void*, int64_t, int, int, cudaStream_t);
 int cast_f32_bf16(const float*, void*, int64_t, cudaStream_t);
 int attn_dense(const void*, int64_t, int, int, int, void*, int64_t, int, int, int, int, float, cudaStream_t);
+int attn_dense_sm100(const void*, int64_t, void*, int64_t, int, int, int, int, float, cudaStream_t);
 int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int, float,
-                  float, float*, float*, cudaStream_t);
+                  float, float*, float*, int, cudaStream_t);
 int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int, float, int, float*, cudaStream_t);
 int rope_inplace(void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int attn_text(const void*, int64_t, const void*, const void*, int64_t, int, int, int, int, int, int, float, float, int, float*,
@@ -83,6 +86,12 @@ int vidi_whisper_im2col2(const void* x, void* out, int C, int T, int d, void* st
 int vidi_pool_s2d(const void* P, void* X, int F, int side, int d, int h, int w, int m, void* stream) {
     return COUNT(vb::pool_s2d(P, X, F, side, d, h, w, m, ST(stream)));
 }
+int vidi_conv_window_gather(const void* P, void* A, int F, int side, int d, int k, void* stream) {
+    return COUNT(vb::conv_window_gather(P, A, F, side, d, k, ST(stream)));
+}
+int vidi_bilinear_ac(const void* X, void* Y, int F, int si, int so, int d, void* stream) {
+    return COUNT(vb::bilinear_ac(X, Y, F, si, so, d, ST(stream)));
+}
 int vidi_embed_gather(const int64_t* ids, const void* E, void* out, int T, int D, int vocab, float normalizer, void* stream) {
     return COUNT(vb::embed_gather(ids, E, out, T, D, vocab, normalizer, ST(stream)));
 }
@@ -97,12 +106,24 @@ int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
 }
 int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,
                     int dh, float scale, void* stream) {
+    // packed Q|K|V projection output with a tower head dim -> tcgen05/TMEM/TMA kernel; anything else -> mma.sync kernel
+    if ((dh == 72 || dh == 64) && q_off == 0 && k_off == H * dh && v_off == 2 * H * dh && ld == (int64_t)3 * H * dh)
+        return COUNT(vb::attn_dense_sm100(qkv, ld, out, ldo, B, S, H, dh, scale, ST(stream)));
+    return COUNT(vb::attn_dense(qkv, ld, q_off, k_off, v_off, out, ldo, B, S, H, dh, scale, ST(stream)));
+}
+int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
+                        int H, int dh, float scale, void* stream) {
     return COUNT(vb::attn_dense(qkv, ld, q_off, k_off, v_off, out, ldo, B, S, H, dh, scale, ST(stream)));
 }
 int vidi_xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
                        int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
                        void* stream) {
-    return COUNT(vb::xattn_splitkv(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, ST(stream)));
+    return COUNT(vb::xattn_splitkv(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, 0, ST(stream)));
+}
+int vidi_xattn_splitkv_mma(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
+                           int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
+                           void* stream) {
+    return COUNT(vb::xattn_splitkv(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, 1, ST(stream)));
 }
 int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per_rank, int64_t rank_stride_o,
                      int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream) {

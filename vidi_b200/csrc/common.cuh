@@ -248,6 +248,13 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     const float k0 = 0.7978845608028654f, k1 = 0.044715f;
     return 0.5f * x * (1.0f + tanhf(k0 * (x + k1 * x * x * x)));
 }
+// GELU-tanh with the hardware tanh.approx (abs err ~5e-4 on tanh -> far below bf16 output rounding); used in GEMM
+// epilogues where 256 activations per thread per tile would otherwise throttle the tile pipeline.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+    const float u = k0 * x * fmaf(k1, x * x, 1.0f);
+    return 0.5f * x * (1.0f + tanh_fast(u));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -37,11 +37,11 @@ struct GemmParams {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-7 epilogue
+constexpr int kNumThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-11 epilogue (2 column halves x 4 lane quarters)
 
 template <int BLOCK_N>
 struct GemmCfg {
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192) ? 5 : 6;
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -93,7 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 128);
+            mbar_init(&tmem_empty[i], 256);
         }
         fence_barrier_init();
     }
@@ -153,7 +153,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;                      // == warp % 4: TMEM lane quarter this warp may access
+        const int ew = (warp - 4) & 3;                // == warp % 4: TMEM lane quarter this warp may access
+        const int wg = (warp - 4) >> 2;               // which half of the tile columns this warp drains
         const int row_in_tile = ew * 32 + lane_id();
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -170,7 +171,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 constexpr int HALF = BLOCK_N / 2;
                 const int col0 = n_blk * HALF;
 #pragma unroll 1
-                for (int c = 0; c < HALF; c += 16) {
+                for (int c = wg * (HALF / 2); c < (wg + 1) * (HALF / 2); c += 16) {
                     uint32_t g[16], u[16];
                     tmem_ld_32x32b_x16(taddr + c, g);
                     tmem_ld_32x32b_x16(taddr + HALF + c, u);
@@ -182,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
                             float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
                             if (p.glu == GLU_GELU_TANH) {
-                                g0 = gelu_tanh(g0); g1 = gelu_tanh(g1);
+                                g0 = gelu_tanh_fast(g0); g1 = gelu_tanh_fast(g1);
                             } else {
                                 g0 = g0 / (1.0f + __expf(-g0)); g1 = g1 / (1.0f + __expf(-g1));
                             }
@@ -205,7 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             } else {
                 const int col0 = n_blk * BLOCK_N;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
+                for (int c = wg * (BLOCK_N / 2); c < (wg + 1) * (BLOCK_N / 2); c += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c, r);
                     tmem_ld_wait();
@@ -232,7 +233,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                         } else if (p.act == ACT_GELU_TANH) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+                            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
                         } else if (p.act == ACT_SOFTCAP) {
                             const float inv = 1.0f / p.act_param;
 #pragma unroll
@@ -334,6 +335,7 @@ int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, i
     p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu; p.group_m = 16;
     if (glu) VB_REQUIRE(N % block_n == 0, "gemm_bf16: GLU needs N %% block_n == 0 (packed gate|up tiles)");
     if (block_n == 256) return launch_gemm<256>(A, lda, W, ldw, p, st);
+    if (block_n == 192) return launch_gemm<192>(A, lda, W, ldw, p, st);
     if (block_n == 128) return launch_gemm<128>(A, lda, W, ldw, p, st);
     if (block_n == 64) return launch_gemm<64>(A, lda, W, ldw, p, st);
     VB_REQUIRE(false, "gemm_bf16: unsupported block_n %d", block_n);

@@ -192,6 +192,71 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Vidi-7B learned pooling (Vidi_7B/model/mm_vision/pool.py:6-26): Conv2d(d->d, k x k, stride 1, no bias) as a GEMM over
+// the window gather below, then bilinear(align_corners=True) to s_out x s_out.
+//   window gather: P [F, side*side, d] -> A [F*so*so, k*k*d], so = side-k+1, A[(f,y,x), (ky*k+kx)*d + c] = P[f,(y+ky)*side+(x+kx),c]
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_window_gather_kernel(const __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ A, int side, int d,
+                                          int k) {
+    const int so = side - k + 1;
+    const int row = blockIdx.x;
+    const int f = row / (so * so), yx = row % (so * so);
+    const int y = yx / so, x = yx % so;
+    const int nvec = d >> 3;
+    for (int i = threadIdx.x; i < k * k * nvec; i += blockDim.x) {
+        const int q = i / nvec, v = i % nvec;
+        const int ky = q / k, kx = q % k;
+        reinterpret_cast<uint4*>(A + (int64_t)row * k * k * d + q * d)[v] =
+            reinterpret_cast<const uint4*>(P + ((int64_t)f * side * side + (y + ky) * side + (x + kx)) * d)[v];
+    }
+}
+// X [F, si, si, d] token-major -> Y [F, so, so, d], PyTorch upsample_bilinear2d with align_corners=True
+__global__ void bilinear_ac_kernel(const __nv_bfloat16* __restrict__ X, __nv_bfloat16* __restrict__ Y, int si, int so, int d) {
+    const int row = blockIdx.x;
+    const int f = row / (so * so), yx = row % (so * so);
+    const int y = yx / so, x = yx % so;
+    const float sc = so > 1 ? (float)(si - 1) / (float)(so - 1) : 0.f;
+    const float sy = sc * (float)y, sx = sc * (float)x;
+    const int y0 = min((int)sy, si - 1), x0 = min((int)sx, si - 1);
+    const int y1 = y0 + (y0 < si - 1 ? 1 : 0), x1 = x0 + (x0 < si - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const __nv_bfloat16* base = X + (int64_t)f * si * si * d;
+    const uint4* s00 = reinterpret_cast<const uint4*>(base + (int64_t)(y0 * si + x0) * d);
+    const uint4* s01 = reinterpret_cast<const uint4*>(base + (int64_t)(y0 * si + x1) * d);
+    const uint4* s10 = reinterpret_cast<const uint4*>(base + (int64_t)(y1 * si + x0) * d);
+    const uint4* s11 = reinterpret_cast<const uint4*>(base + (int64_t)(y1 * si + x1) * d);
+    uint4* o = reinterpret_cast<uint4*>(Y + (int64_t)row * d);
+    for (int v = threadIdx.x; v < (d >> 3); v += blockDim.x) {
+        const uint4 a = s00[v], b = s01[v], c = s10[v], e = s11[v];
+        const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w},
+                       ee[4] = {e.x, e.y, e.z, e.w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = unpack_bf16(aa[j]), fb = unpack_bf16(bb[j]), fc = unpack_bf16(cc[j]), fe = unpack_bf16(ee[j]);
+            r[j] = pack_bf16(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fe.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fe.y);
+        }
+        o[v] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+int conv_window_gather(const void* P, void* A, int F, int side, int d, int k, cudaStream_t st) {
+    VB_REQUIRE(d % 8 == 0 && k >= 1 && k <= side, "conv_window_gather: d=%d k=%d side=%d", d, k, side);
+    if (F == 0) return 0;
+    const int so = side - k + 1;
+    conv_window_gather_kernel<<<F * so * so, 128, 0, st>>>((const __nv_bfloat16*)P, (__nv_bfloat16*)A, side, d, k);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int bilinear_ac(const void* X, void* Y, int F, int si, int so, int d, cudaStream_t st) {
+    VB_REQUIRE(d % 8 == 0 && si >= 1 && so >= 1, "bilinear_ac: d=%d si=%d so=%d", d, si, so);
+    if (F == 0) return 0;
+    bilinear_ac_kernel<<<F * so * so, 128, 0, st>>>((const __nv_bfloat16*)X, (__nv_bfloat16*)Y, si, so, d);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 int patch_im2col(const void* img, void* out, int F, int S, int patch, int Kpad, cudaStream_t st) {
     const int side = S / patch;
     if (F == 0) return 0;

@@ -61,9 +61,13 @@ def _split(n: int, world: int, rank: int):
 
 
 def make_plan(cfg, n_frames: int, n_chunks: int, audio_size: int, rank: int = 0, world: int = 1) -> ShardPlan:
-    hw = cfg.image_hw(n_frames) if n_frames else (28, 28)
-    m = cfg.mm_image_pool_size
-    tpf = (hw[0] // m) * (hw[1] // m)
+    if hasattr(cfg, "image_hw"):                 # Vidi1.5: pad/resize + space-to-depth
+        hw = cfg.image_hw(n_frames) if n_frames else (28, 28)
+        m = cfg.mm_image_pool_size
+        tpf = (hw[0] // m) * (hw[1] // m)
+    else:                                        # Vidi-7B: learned conv pool to pool x pool tokens per frame
+        hw = (cfg.mm_image_pool_size, cfg.mm_image_pool_size)
+        tpf = cfg.mm_image_pool_size ** 2
     f0, f1 = _split(n_frames, world, rank)
     c0, c1 = _split(n_chunks, world, rank)
     ratio = cfg.aud.max_source_positions / cfg.aud.nb_max_frames
@@ -85,8 +89,11 @@ class Vidi15Engine:
         self.device = torch.device(device)
         self.rank, self.world, self.group = rank, world, group
         self.W = load_vidi15(state_dict, cfg, self.device, ops, pop=pop_state_dict)
-        # torch.tensor(hidden**0.5, dtype=act): the normaliser is rounded to the activation dtype (gemma.py:353)
-        self.normalizer = float(torch.tensor(cfg.llm.hidden ** 0.5, dtype=BF16).float())
+        # Gemma2 family (Vidi1.5) vs Mistral family (Vidi-7B): SURVEY.md 3.3
+        self.gemma = hasattr(cfg.llm, "final_softcap")
+        # torch.tensor(hidden**0.5, dtype=act): the normaliser is rounded to the activation dtype (gemma.py:353); Mistral has none
+        self.normalizer = float(torch.tensor(cfg.llm.hidden ** 0.5, dtype=BF16).float()) if self.gemma else 1.0
+        self.glu = ops.GLU_GELU_TANH if self.gemma else ops.GLU_SILU
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
@@ -156,12 +163,19 @@ class Vidi15Engine:
         for s in range(0, fl, self.vit_chunk):
             e = min(fl, s + self.vit_chunk)
             P = self.siglip(images[s:e])
-            X = ops.pool_s2d(P, e - s, v.side, h, w, m)
+            if self.gemma:
+                X = ops.pool_s2d(P, e - s, v.side, h, w, m)
+            else:                                    # Vidi_7B/model/mm_vision/pool.py:20-26
+                k = self.W.img_pool_k
+                A = ops.conv_window_gather(P, e - s, v.side, k)
+                Y = ops.gemm(A, self.W.img_pool_w, tag="tower")
+                X = ops.bilinear_ac(Y, e - s, v.side - k + 1, m)
+                del A, Y
             del P
             hid = ops.gemm(X, self.W.img_proj.w1, bias=self.W.img_proj.b1, act=ops.ACT_GELU_ERF)
             ops.gemm(hid, self.W.img_proj.w2, bias=self.W.img_proj.b2, out=proj[s * plan.tpf:e * plan.tpf])
             del X, hid
-        hp, wp = h // m, w // m
+        hp, wp = (h // m, w // m) if self.gemma else (m, m)
         th = self.pos_table("h", hp, 0, hp, m)
         tw = self.pos_table("w", wp, 0, wp, m)
         tt = self.pos_table("t", fl, plan.f0, plan.F, cfg.mm_time_interval)
@@ -203,7 +217,8 @@ class Vidi15Engine:
             kv = torch.empty(len(Ls), n, 2 * c.kv_dim, device=self.device, dtype=BF16)
         if n == 0:
             return kv
-        h = ops.rmsnorm(S, Ls[0].n_in, c.rms_eps, True)
+        gm = self.gemma
+        h = ops.rmsnorm(S, Ls[0].n_in, c.rms_eps, gm)
         y = torch.empty_like(S)
         g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
@@ -211,10 +226,16 @@ class Vidi15Engine:
             if l == len(Ls) - 1:
                 break
             ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo")
-            ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
-            ops.gemm(h, L.wgu, glu=ops.GLU_GELU_TANH, out=g, tag="llm_gateup")
+            if gm:      # S += G(y, w_post); h = G(S, w_preff)          (gemma.py:198-202,116-118)
+                ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
+            else:       # S += y; h = norm(S, w_post_attention)          (mistral.py:223-225,131-133)
+                ops.residual_norm(S, y, None, L.n_post, h, c.rms_eps, 0, False)
+            ops.gemm(h, L.wgu, glu=self.glu, out=g, tag="llm_gateup")
             ops.gemm(g, L.wd, out=y, tag="llm_down")
-            ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
+            if gm:
+                ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
+            else:
+                ops.residual_norm(S, y, None, Ls[l + 1].n_in, h, c.rms_eps, 0, False)
         return kv
 
     # ------------------------------------------------------------------------------------------
@@ -236,11 +257,12 @@ class Vidi15Engine:
         if text_cache is not None:
             pos0 = text_cache["len"]
             assert pos0 + Tq <= text_cache["kv"].shape[1], "text KV cache too small"
-        scale = c.query_pre_attn_scalar ** -0.5 if hasattr(c, "query_pre_attn_scalar") else dh ** -0.5
-        cap = getattr(c, "attn_softcap", 0.0) or 0.0
+        gm = self.gemma
+        scale = c.query_pre_attn_scalar ** -0.5 if gm else dh ** -0.5
+        cap = (c.attn_softcap or 0.0) if gm else 0.0
         Ls = self.W.layers
         H = ops.embed_gather(ids, self.W.embed, self.normalizer)
-        h = ops.rmsnorm(H, Ls[0].n_in, c.rms_eps, True)
+        h = ops.rmsnorm(H, Ls[0].n_in, c.rms_eps, gm)
         rows = Tq * c.heads
         # one flat fp32 buffer per layer holds every stream's [O | LSE] partials of this rank
         splits = [ops.xattn_splits(-(-s[4] // self.world), c.kv_heads, self.n_sms) for s in seg]
@@ -262,7 +284,7 @@ class Vidi15Engine:
                 kview, vview, Tk = krope[:, :kd], krope[:, kd:], Tq
             qrope = qkv[:, :qd].clone()
             ops.rope_inplace(qrope, 0, c.heads, dh, self.W.inv_freq, pos0)
-            window = c.sliding_window if (hasattr(c, "sliding_window") and l % 2 == 0) else 0
+            window = (c.sliding_window if l % 2 == 0 else 0) if gm else (getattr(c, "sliding_window", 0) or 0)
             ops.attn_text(qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, scale, cap, window, out=att)
             off = 0
             for (r0, nr, kmask, gate, _), sp, sz in zip(seg, splits, sizes):
@@ -283,15 +305,23 @@ class Vidi15Engine:
             a = ops.cast_bf16(att)
             ops.gemm(a, L.wo, out=y, tag="text")
             h2 = torch.empty_like(H)
-            ops.residual_norm(H, y, L.n_post, L.n_preff, h2, c.rms_eps, 1, True)
-            g = ops.gemm(h2, L.wgu, glu=ops.GLU_GELU_TANH, tag="text")
-            ops.gemm(g, L.wd, out=y, tag="text")
             w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else self.W.final_norm
-            ops.residual_norm(H, y, L.n_postff, w_next, h, c.rms_eps, 1, True)
+            if gm:
+                ops.residual_norm(H, y, L.n_post, L.n_preff, h2, c.rms_eps, 1, True)
+            else:       # H = residual + (a_t + a_i + a_a) W_o^T ; h2 = post_attention_layernorm(H)   (mistral.py:263,131-133)
+                ops.residual_norm(H, y, None, L.n_post, h2, c.rms_eps, 0, False)
+            g = ops.gemm(h2, L.wgu, glu=self.glu, tag="text")
+            ops.gemm(g, L.wd, out=y, tag="text")
+            if gm:
+                ops.residual_norm(H, y, L.n_postff, w_next, h, c.rms_eps, 1, True)
+            else:
+                ops.residual_norm(H, y, None, w_next, h, c.rms_eps, 0, False)
         if text_cache is not None:
             text_cache["len"] = pos0 + Tq
         hn = h if not logits_to_keep else h[-logits_to_keep:]
-        return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True, tag="text")
+        if gm:          # 30 * tanh(logits / 30)   (gemma.py:566-569)
+            return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True, tag="text")
+        return ops.gemm(hn, self.W.lm_head, out_fp32=True, tag="text")      # logits.float() (mistral.py:615-616)
 
     # ------------------------------------------------------------------------------------------
     # whole prefill for one sample

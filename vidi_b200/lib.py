@@ -28,12 +28,16 @@ SIGNATURES = {
     "vidi_whisper_im2col1": [_p, _p, _i, _i, _i, _p],
     "vidi_whisper_im2col2": [_p, _p, _i, _i, _i, _p],
     "vidi_pool_s2d": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "vidi_conv_window_gather": [_p, _p, _i, _i, _i, _i, _p],
+    "vidi_bilinear_ac": [_p, _p, _i, _i, _i, _i, _p],
     "vidi_embed_gather": [_p, _p, _p, _i, _i, _i, _f, _p],
     "vidi_sinusoid_split": [_p, _p, _i, _i, _i, _i, _i, _p],
     "vidi_split3": [_p, _p, _l, _i, _i, _p],
     "vidi_cast_f32_bf16": [_p, _p, _l, _p],
     "vidi_attn_dense": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
+    "vidi_attn_dense_mma": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_xattn_splitkv": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "vidi_xattn_splitkv_mma": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_merge": [_p, _p, _i, _i, _l, _l, _i, _i, _f, _i, _p, _p],
     "vidi_rope_inplace": [_p, _l, _i, _i, _i, _i, _p, _i, _p],
     "vidi_attn_text": [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p],

@@ -73,11 +73,14 @@ class DattnGemma2ForCausalLM:
         self.device = self.engine.device
         self.dtype = BF16
         c = cfg.llm
-        self.config = SimpleNamespace(mm_splits=cfg.mm_splits, eos_token_id=107, pad_token_id=0, vocab_size=c.vocab,
-                                      hidden_size=c.hidden, num_hidden_layers=c.layers, mm_input_type="video",
-                                      mm_image_pool_size=cfg.mm_image_pool_size, mm_audio_pool_size=cfg.mm_audio_pool_size,
-                                      mm_time_interval=cfg.mm_time_interval, final_logit_softcapping=c.final_softcap,
-                                      model_type="dattn_gemma2")
+        gemma = hasattr(c, "final_softcap")
+        # eos: 107 for the Gemma2 build (gemma.py:461-462); Mistral keeps the tokenizer's </s> = 2
+        self.config = SimpleNamespace(mm_splits=cfg.mm_splits, eos_token_id=107 if gemma else 2, pad_token_id=0,
+                                      vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers,
+                                      mm_input_type="video", mm_image_pool_size=cfg.mm_image_pool_size,
+                                      mm_audio_pool_size=cfg.mm_audio_pool_size, mm_time_interval=cfg.mm_time_interval,
+                                      final_logit_softcapping=getattr(c, "final_softcap", None),
+                                      model_type="dattn_gemma2" if gemma else "dattn_mistral")
         self._mm = SimpleNamespace(text_tokenizer=tokenizer, image_processor=image_processor, audio_processor=audio_processor)
         self.training = False
 
@@ -224,6 +227,11 @@ class DattnGemma2ForCausalLM:
         for b, s in enumerate(seqs):
             out[b, :len(s)] = torch.tensor(s, dtype=torch.long)
         return out.to(self.device)
+
+
+class DattnMistralForCausalLM(DattnGemma2ForCausalLM):
+    """Vidi-7B twin (Vidi_7B/model/lmm/dattn/mistral.py:496-713): same surface, Mistral-family engine paths
+    (selected by the config type: SwiGLU, no post-norms / soft-caps / normaliser, learned-conv pooling, fp32 logits)."""
 
 
 # -------------------------------------------------------------------------------------------------

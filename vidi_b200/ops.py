@@ -38,6 +38,8 @@ def _rowmajor(t: torch.Tensor) -> int:
 def pick_block_n(M: int, N: int, glu: bool = False) -> int:
     if glu:
         return 256
+    if N % 256 != 0 and N % 192 == 0 and N < 2048:
+        return 192                      # 1152, 3456: exact tiling instead of a half-empty last 256 tile
     if N >= 1024 or N % 256 == 0:
         return 256
     return 128 if N > 64 else 64
@@ -176,6 +178,25 @@ def pool_s2d(P, F_: int, side: int, h: int, w: int, m: int):
     return out
 
 
+def conv_window_gather(P, F_: int, side: int, k: int):
+    L = _lib.load()
+    d = P.shape[-1]
+    so = side - k + 1
+    assert P.dtype == BF16 and P.is_contiguous() and P.numel() == F_ * side * side * d
+    out = torch.empty(F_ * so * so, k * k * d, device=P.device, dtype=BF16)
+    _lib.check(L.vidi_conv_window_gather(_ptr(P), _ptr(out), F_, side, d, k, _stream()), "conv_window_gather")
+    return out
+
+
+def bilinear_ac(X, F_: int, si: int, so: int):
+    L = _lib.load()
+    d = X.shape[-1]
+    assert X.dtype == BF16 and X.is_contiguous() and X.numel() == F_ * si * si * d
+    out = torch.empty(F_ * so * so, d, device=X.device, dtype=BF16)
+    _lib.check(L.vidi_bilinear_ac(_ptr(X), _ptr(out), F_, si, so, d, _stream()), "bilinear_ac")
+    return out
+
+
 def embed_gather(ids, E, normalizer: float):
     L = _lib.load()
     assert ids.dtype == torch.int64 and ids.is_contiguous() and E.dtype == BF16 and E.is_contiguous()
@@ -211,15 +232,16 @@ def cast_bf16(x):
     return y
 
 
-def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None):
-    """qkv [B*S, 3*H*dh] with Q|K|V sections -> out [B*S, H*dh]."""
+def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None, impl: str = "auto"):
+    """qkv [B*S, 3*H*dh] with Q|K|V sections -> out [B*S, H*dh].  impl: "auto" (tcgen05 for dh 64/72) | "mma"."""
     L = _lib.load()
     d = H * dh
     assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
     if out is None:
         out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
-    _lib.check(L.vidi_attn_dense(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale,
-                                 _stream()), "attn_dense")
+    fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense
+    _lib.check(fn(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale, _stream()),
+               "attn_dense")
     return out
 
 
@@ -232,7 +254,7 @@ def xattn_splits(n_keys: int, hkv: int, n_sms: int = 148) -> int:
 
 
 def xattn_splitkv(q, k, v, kmask, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, splits: int,
-                  opart=None, lse=None):
+                  opart=None, lse=None, impl: str = "auto"):
     """q [T, Hq*dh]; k,v [N, *] views with row stride ld -> (opart [splits,T,Hq,dh] f32, lse [splits,T,Hq] f32)."""
     L = _lib.load()
     T = q.shape[0]
@@ -242,9 +264,9 @@ def xattn_splitkv(q, k, v, kmask, Hq: int, Hkv: int, dh: int, scale: float, soft
     if opart is None:
         opart = torch.empty(splits, T, Hq, dh, device=q.device, dtype=torch.float32)
         lse = torch.empty(splits, T, Hq, device=q.device, dtype=torch.float32)
-    _lib.check(L.vidi_xattn_splitkv(_ptr(q), _rowmajor(q), _ptr(k), _ptr(v), k.stride(0) if N else 8, _ptr(kmask), T, N,
-                                    Hq, Hkv, dh, splits, scale, softcap, _ptr(opart), _ptr(lse), _stream()),
-               "xattn_splitkv")
+    fn = L.vidi_xattn_splitkv_mma if impl == "mma" else L.vidi_xattn_splitkv
+    _lib.check(fn(_ptr(q), _rowmajor(q), _ptr(k), _ptr(v), k.stride(0) if N else 8, _ptr(kmask), T, N,
+                  Hq, Hkv, dh, splits, scale, softcap, _ptr(opart), _ptr(lse), _stream()), "xattn_splitkv")
     return opart, lse
 
 

@@ -100,9 +100,7 @@ def tensor_specs(cfg) -> dict:
         import math
         k = math.ceil(V.side / cfg.mm_image_pool_size)
         s["model.mm_rand_img_pool.conv.weight"] = ((V.hidden, V.hidden, k, k), "normal", 0.02 / k, False)
-        s["model.mm_rand_img_pool.conv.bias"] = ((V.hidden,), "normal", 0.02, False)
         s["model.mm_rand_aud_pool.weight"] = ((A.d_model, A.d_model, cfg.mm_audio_pool_size), "normal", 0.02, False)
-        s["model.mm_rand_aud_pool.bias"] = ((A.d_model,), "normal", 0.02, False)
         pin = V.hidden
         aud_proj_in = A.d_model
     lin("model.mm_rand_img_projector.model.0", D, pin, bias=True)

@@ -129,8 +129,13 @@ def load_vidi15(sd: dict, cfg, device, ops, pop: bool = False):
                layers=[load_tower_layer(sd, f"{pa}.layers.{l}", device, WHISPER_NAMES, pop=pop) for l in range(a.layers)])
     # mm glue
     m = cfg.mm_image_pool_size
-    w1 = sd["model.mm_rand_img_projector.model.0.weight"]                       # [D, dv*m*m] columns c*m*m + q
-    w1 = w1.reshape(D, v.hidden, m * m).permute(0, 2, 1).reshape(D, m * m * v.hidden)   # -> q*dv + c
+    w1 = sd["model.mm_rand_img_projector.model.0.weight"]
+    if "model.mm_rand_img_pool.conv.weight" in sd:                              # Vidi-7B learned pool: conv as GEMM
+        wc = sd["model.mm_rand_img_pool.conv.weight"]                           # [dv, dv, k, k] -> columns (ky*k+kx)*dv + c
+        W.img_pool_k = wc.shape[-1]
+        W.img_pool_w = _dev(wc.permute(0, 2, 3, 1).reshape(wc.shape[0], -1), device, BF16)
+    else:                                                                       # Vidi1.5: [D, dv*m*m], columns c*m*m + q
+        w1 = w1.reshape(D, v.hidden, m * m).permute(0, 2, 1).reshape(D, m * m * v.hidden)   # -> q*dv + c
     W.img_proj = NS(w1=_dev(w1, device, BF16), b1=_dev(sd["model.mm_rand_img_projector.model.0.bias"], device, torch.float32),
                     w2=_dev(sd["model.mm_rand_img_projector.model.2.weight"], device, BF16),
                     b2=_dev(sd["model.mm_rand_img_projector.model.2.bias"], device, torch.float32))
