@@ -44,6 +44,11 @@ int vidi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
                    int out_fp32, int glu, int block_n, void* stream);
 
+/* same contract on a CTA pair (tcgen05 cta_group::2, 256 x block_n tile per pair, block_n in {128,256}) */
+int vidi_gemm_bf16_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                        const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                        int out_fp32, int glu, int block_n, void* stream);
+
 /* y = x_hat(x,eps) * (add_one ? 1+w : w) * out_scale.  Gemma2RMSNorm (gemma.py:107-111,162,184) / vidi RMSNorm (mm_layer/norm.py:17-25) */
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream);

@@ -205,6 +205,20 @@ for l in range(2):
     hs, im, au = hs_out, im_out, au_out
 OUT["decoder"] = dict(ids=ids, H0=H0[0], img0=img0[0], aud0=aud0[0], layers=layer_out)
 
+# ---------------------------------------------------------------- Vidi-7B learned pool (Vidi_7B/model/mm_vision/pool.py)
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("vidi7b_pool", "/root/reference/Vidi_7B/model/mm_vision/pool.py")
+_pool7 = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_pool7)
+with torch.no_grad():
+    x7 = rnd(2, 6, 27, 27)
+    out7 = {}
+    for s_out in (16, 4, 9):
+        m7 = _pool7.Conv2DPool(6, 6, 27, s_out).eval()
+        out7[s_out] = dict(w=m7.conv.weight.data.clone(), out=m7(x7))
+    OUT["pool7b"] = dict(x=x7, cases=out7)
+
 torch.save(OUT, os.path.join(HERE, "vidi15_reference_golden.pt"))
 sz = os.path.getsize(os.path.join(HERE, "vidi15_reference_golden.pt"))
 print(f"wrote vidi15_reference_golden.pt ({sz / 1e6:.2f} MB); keys: {list(OUT)}")

@@ -41,6 +41,31 @@ def test_gemm_plain(M, N, K, bn):
     assert float((out.float() - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (256, 128, 128, 128), (300, 520, 288, 256), (1000, 1152, 640, 128),
+                                      (4096, 4096, 3584, 256), (5000, 4304, 1152, 256), (129, 72, 64, 128), (46656, 1152, 1152, 128), (3000, 1152, 4304, 192),
+                                      (700, 3456, 1152, 192)])
+def test_gemm_2cta(M, N, K, bn):
+    """CTA-pair (cta_group::2) kernel: same contract as the 1-CTA kernel."""
+    from vidi_b200 import ops
+    a = rnd(M, K, seed=51).to(BF); w = rnd(N, K, scale=0.05, seed=52).to(BF)
+    bias = rnd(N, seed=53).float(); res = rnd(M, N, seed=54).to(BF)
+    out = ops.gemm(a, w, bias=bias, residual=res, act=2, block_n=bn, cta2=True)
+    ref = F.gelu(a.float() @ w.float().t() + bias, approximate="tanh") + res.float()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+
+
+def test_gemm_2cta_glu():
+    from vidi_b200 import ops
+    from vidi_b200.weights import pack_glu
+    M, I, K = 1300, 1024, 512
+    a = rnd(M, K, seed=55).to(BF)
+    wg = rnd(I, K, scale=0.05, seed=56).to(BF); wu = rnd(I, K, scale=0.05, seed=57).to(BF)
+    out = ops.gemm(a, pack_glu(wg, wu, 256), glu=1, block_n=256, cta2=True)
+    ref = F.gelu(a.float() @ wg.float().t(), approximate="tanh") * (a.float() @ wu.float().t())
+    assert out.shape == (M, I) and rel_err(out, ref) < 8e-3
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
 def test_gemm_epilogues(act):
     from vidi_b200 import ops

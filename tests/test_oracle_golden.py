@@ -97,3 +97,21 @@ def test_prefill_consistency_with_layer_fixture():
     logits, inter = R.prefill(sd, cfg, ids, images, mels, asz, return_intermediates=True)
     close(inter["text_hidden"][-1], G["decoder"]["layers"][-1]["text"], 5e-5)
     assert logits.shape == (6, cfg.llm.vocab) and float(logits.abs().max()) <= 30.0
+
+
+def test_vidi7b_conv_pool_matches_reference():
+    """Vidi_7B/model/mm_vision/pool.py Conv2DPool (learned conv + align_corners bilinear), run from the reference file."""
+    from oracle import vidi7b_ref as R7
+    g = G["pool7b"]
+    for s_out, case in g["cases"].items():
+        close(R7.conv2d_pool_7b(g["x"], case["w"], s_out), case["out"], 1e-6)
+
+
+def test_vidi7b_oracle_runs_and_shapes():
+    from oracle import vidi7b_ref as R7
+    from vidi_b200.config import vidi7b_mini
+    cfg = vidi7b_mini()
+    sd = synth.make_state_dict(cfg, seed=5)
+    ids, images, mels, asz = synth.make_inputs(cfg, 2, 1, n_text=7, audio_size=900)
+    logits = R7.prefill(sd, cfg, ids, images, mels, asz)
+    assert logits.shape == (7, cfg.llm.vocab) and torch.isfinite(logits).all()

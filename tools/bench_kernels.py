@@ -31,12 +31,19 @@ def gemm_case(name, M, N, K, glu=0, bn=None):
     a = torch.randn(M, K, device="cuda").to(BF)
     w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
     out = torch.empty(M, N // 2 if glu else N, device="cuda", dtype=BF)
-    t = timeit(lambda: ops.gemm(a, w, out=out, glu=glu, block_n=bn))
+    t = timeit(lambda: ops.gemm(a, w, out=out, glu=glu, block_n=bn, cta2=False))
+    t2 = {}
+    if M >= 1024:
+        for b2 in (256, 192):
+            try:
+                t2[b2] = round(2.0 * M * N * K / timeit(lambda: ops.gemm(a, w, out=out, glu=glu, block_n=b2, cta2=True)) / 1e9, 1)
+            except Exception as ex:  # noqa: BLE001
+                t2[b2] = repr(ex)[:60]
     ref = torch.empty(M, N, device="cuda", dtype=BF)
     t_ref = timeit(lambda: torch.matmul(a, w.t(), out=ref))
     fl = 2.0 * M * N * K
     print(json.dumps(dict(kernel="gemm", name=name, M=M, N=N, K=K, glu=glu, ms=round(t, 4), tflops=round(fl / t / 1e9, 1),
-                          cublas_ms=round(t_ref, 4), cublas_tflops=round(fl / t_ref / 1e9, 1))), flush=True)
+                          cublas_ms=round(t_ref, 4), cublas_tflops=round(fl / t_ref / 1e9, 1), cta2_tflops=t2)), flush=True)
 
 
 def xattn_case(T, N, splits=None):

@@ -9,6 +9,8 @@ namespace vb {
 const char* last_error();
 int gemm_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
               int, int, float, int, int, int, cudaStream_t);
+int gemm2_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
+               int, int, float, int, int, int, cudaStream_t);
 int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, int, float, cudaStream_t);
 int residual_norm(void*, int64_t, const void*, int64_t, const void*, const void*, void*, int64_t, int, int, float, int, int,
                   cudaStream_t);
@@ -52,6 +54,12 @@ int vidi_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
                    int out_fp32, int glu, int block_n, void* stream) {
     return COUNT(vb::gemm_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, out_fp32, glu,
                                block_n, ST(stream)));
+}
+int vidi_gemm_bf16_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                        const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                        int out_fp32, int glu, int block_n, void* stream) {
+    return COUNT(vb::gemm2_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, out_fp32, glu,
+                                block_n, ST(stream)));
 }
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream) {

@@ -1,0 +1,248 @@
+// 2-CTA (cta_group::2) variant of the persistent bf16 GEMM: a CTA pair on one TPC computes a 256 x BLOCK_N tile.
+//
+//   * each CTA TMA-loads its own 128 rows of A and HALF of the W tile (BLOCK_N/2 rows); the pair's tcgen05.mma
+//     (M=256, issued by the leader CTA only) reads A from both CTAs' shared memory and the two W halves across the
+//     pair, so per-CTA L2->SMEM traffic per flop drops by a third versus the 1-CTA 128 x 256 tile and the
+//     stage gets small enough for a 6-deep ring;
+//   * all TMA transactions of both CTAs complete on the LEADER's full barrier (peer bit cleared in the mbarrier
+//     address); tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs;
+//   * each CTA drains its own 128 TMEM lanes with the shared epilogue; the follower's epilogue threads release the
+//     accumulator on the leader's barrier through a shared::cluster arrive.
+#include "gemm_epilogue.cuh"
+
+namespace vb {
+namespace g2 {
+
+constexpr int BLOCK_M = 128;        // per CTA; the pair covers 256 rows
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 384;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
+    static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;      // this CTA's half of W
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kTmemCols = 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the same barrier offset in both CTAs of the pair when all prior MMAs of this thread are done
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int gm = min(group_m, num_m - first_m);
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % gm;
+    n_blk = r / gm;
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + C::kStages * C::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* full_bar = bars;                     // [kStages]  used on the leader only (TMA of both CTAs -> leader MMA)
+    uint64_t* empty_bar = bars + C::kStages;       // [kStages]  per CTA (MMA commit multicast -> each producer)
+    uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]        per CTA (commit multicast -> each epilogue)
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]        used on the leader only (both epilogues -> MMA)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < C::kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 2 * 256);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2sm<C::kTmemCols>(tmem_ptr);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                int m_blk, n_blk;
+                tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+                const int row_a = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M;
+                const int row_b = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                    tma_load_2d_2sm(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K, row_a);
+                    tma_load_2d_2sm(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K, row_b);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(smem_a + stage * C::kABytes));
+                    const uint64_t b_desc = umma_desc_k_sw128(smem_u32(smem_b + stage * C::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_f16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int ew = (warp - 4) & 3;
+        const int wg = (warp - 4) >> 2;
+        const int row_in_tile = (int)rank * BLOCK_M + ew * 32 + lane_id();
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            int m_blk, n_blk;
+            tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * 2 * BLOCK_M + row_in_tile;
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
+            epilogue_tile<BLOCK_N>(p, taddr, row, n_blk, wg);
+            tc_fence_before();
+            mbar_arrive_leader(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm<C::kTmemCols>(tmem_base);
+    }
+}
+
+template <int BLOCK_N>
+static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BLOCK_N>;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
+    if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N / 2))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        attr_set = true;
+    }
+    const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int tiles = num_m * num_n;
+    const int max_pairs = num_sms() / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    gemm2_bf16_kernel<BLOCK_N><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace g2
+
+// same contract as gemm_bf16 (gemm_sm100.cu); block_n in {128, 256}; GLU tiles: each CTA's W half must hold whole
+// [gate | up] groups, so the packed group width is block_n/2 (see weights.pack_glu) -- handled by the caller.
+int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+               const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
+               int glu, int block_n, cudaStream_t st) {
+    VB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm2_bf16: empty problem");
+    VB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm2_bf16: K/lda/ldw/ldc must be multiples of 8");
+    if (glu) VB_REQUIRE(N % block_n == 0, "gemm2_bf16: GLU needs N %% block_n == 0 (packed gate|up tiles)");
+    g2::GemmParams p;
+    p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.res_mod = res_mod;
+    p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu; p.group_m = 8;
+    if (block_n == 256) return g2::launch<256>(A, lda, W, ldw, p, st);
+    if (block_n == 192) return g2::launch<192>(A, lda, W, ldw, p, st);
+    if (block_n == 128) return g2::launch<128>(A, lda, W, ldw, p, st);
+    VB_REQUIRE(false, "gemm2_bf16: unsupported block_n %d", block_n);
+}
+
+}  // namespace vb

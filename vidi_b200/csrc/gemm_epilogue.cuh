@@ -1,0 +1,154 @@
+// Epilogue of the bf16 GEMM family (shared by the 2-CTA kernel): one call drains this warp's share of one
+// accumulator tile from TMEM and applies bias / activation / GLU / residual / soft-cap, storing bf16 or fp32 rows.
+#pragma once
+#include "common.cuh"
+
+namespace vb {
+namespace g2 {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_SOFTCAP = 3, ACT_SILU = 4 };
+enum Glu : int { GLU_NONE = 0, GLU_GELU_TANH = 1, GLU_SILU = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    void* C;
+    int64_t ldc;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    int64_t ldr;
+    int res_mod;
+    int act;
+    float act_param;
+    int out_fp32;
+    int glu;
+    int group_m;
+};
+
+// taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;
+// wg: which half of the tile columns this warp drains; n_blk: tile column index.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int n_blk, int wg) {
+    const bool row_ok = row < p.M;
+    const int out_cols_total = p.glu ? p.N / 2 : p.N;
+    if (p.glu) {
+        constexpr int HALF = BLOCK_N / 2;
+        const int col0 = n_blk * HALF;
+#pragma unroll 1
+        for (int c = wg * (HALF / 2); c < (wg + 1) * (HALF / 2); c += 16) {
+            uint32_t g[16], u[16];
+            tmem_ld_32x32b_x16(taddr + c, g);
+            tmem_ld_32x32b_x16(taddr + HALF + c, u);
+            tmem_ld_wait();
+            if (row_ok && col0 + c < out_cols_total) {
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+                    float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
+                    if (p.glu == GLU_GELU_TANH) {
+                        g0 = gelu_tanh_fast(g0); g1 = gelu_tanh_fast(g1);
+                    } else {
+                        g0 = g0 / (1.0f + __expf(-g0)); g1 = g1 / (1.0f + __expf(-g1));
+                    }
+                    o[j] = pack_bf16(g0 * u0, g1 * u1);
+                }
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0 + c;
+                if (col0 + c + 16 <= out_cols_total) {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 pr = *reinterpret_cast<__nv_bfloat162*>(&o[j]);
+                        if (col0 + c + 2 * j < out_cols_total) dst[2 * j] = pr.x;
+                        if (col0 + c + 2 * j + 1 < out_cols_total) dst[2 * j + 1] = pr.y;
+                    }
+                }
+            }
+        }
+    } else {
+        const int col0 = n_blk * BLOCK_N;
+#pragma unroll 1
+        for (int c = wg * (BLOCK_N / 2); c < (wg + 1) * (BLOCK_N / 2); c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c, r);
+            tmem_ld_wait();
+            const int cbase = col0 + c;
+            if (row_ok && cbase < p.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const bool full = cbase + 32 <= p.N;
+                if (p.bias) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.bias + cbase + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += p.bias[cbase + j];
+                    }
+                }
+                if (p.act == ACT_GELU_ERF) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                } else if (p.act == ACT_GELU_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+                } else if (p.act == ACT_SOFTCAP) {
+                    const float inv = 1.0f / p.act_param;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = p.act_param * tanhf(v[j] * inv);
+                } else if (p.act == ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+                }
+                if (p.residual) {
+                    const __nv_bfloat16* rp = p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr + cbase;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                            float2 f;
+                            f = unpack_bf16(q.x); v[j] += f.x; v[j + 1] += f.y;
+                            f = unpack_bf16(q.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                            f = unpack_bf16(q.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                            f = unpack_bf16(q.w); v[j + 6] += f.x; v[j + 7] += f.y;
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] += __bfloat162float(rp[j]);
+                    }
+                }
+                if (p.out_fp32) {
+                    float* dst = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + cbase;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = v[j];
+                    }
+                } else {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + cbase;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(dst + j) =
+                                make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                           pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = __float2bfloat16(v[j]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace g2
+}  // namespace vb

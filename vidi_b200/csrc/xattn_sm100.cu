@@ -30,7 +30,7 @@ struct XsCfg {
     static constexpr int kStage = 2 * kKBytes;                 // K + V
     static constexpr int kPBytes = 128 * 128;                  // [128 rows][64 keys] bf16 = 16 KB
     static constexpr int kOffQ = 0, kOffKV = kQBytes, kOffP = kOffKV + 2 * kStage, kOffBar = kOffP + 2 * kPBytes;
-    static constexpr int kSmem = kOffBar + 128 + 1024;
+    static constexpr int kSmem = kOffBar + 192 + 1024;
     static constexpr int kTmemO = 128;                         // O columns start (S buffers at 0 and 64)
 };
 
@@ -55,14 +55,16 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
     uint64_t* q_full = bars;          // [1]
-    uint64_t* kv_full = bars + 1;     // [2]
-    uint64_t* kv_empty = bars + 3;    // [2]
+    uint64_t* k_full = bars + 1;      // [2]   K and V tiles have separate rings: a K slot is released as soon as its
+    uint64_t* k_empty = bars + 3;     // [2]   QK^T has been issued, without waiting for softmax + PV of that tile
     uint64_t* s_full = bars + 5;      // [2]
     uint64_t* s_empty = bars + 7;     // [2] (256 arrivals)
     uint64_t* p_full = bars + 9;      // [2] (256 arrivals)
     uint64_t* p_empty = bars + 11;    // [2]
     uint64_t* o_full = bars + 13;     // [1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* v_full = bars + 14;     // [2]
+    uint64_t* v_empty = bars + 16;    // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int split = blockIdx.x, hk = blockIdx.y, qb = blockIdx.z;
     const int warp = threadIdx.x >> 5;
@@ -77,7 +79,8 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     if (warp == 1 && elect_one()) {
         mbar_init(q_full, 1); mbar_init(o_full, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 256);
             mbar_init(&p_full[i], 256); mbar_init(&p_empty[i], 1);
         }
@@ -90,21 +93,32 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
+        // Q + K producer
         if (elect_one() && ntiles > 0) {
             mbar_expect_tx(q_full, C::kQBytes);
             for (int a = 0; a < C::ATOMS; ++a)
                 tma_load_3d(smem + C::kOffQ + a * C::kAtomQ, &tm_q, q_full, a * 64, hk * p.G, t0, kEvictLast);
             for (int j = 0; j < ntiles; ++j) {
                 const int st = j & 1;
-                mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-                mbar_expect_tx(&kv_full[st], C::kStage);
+                mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&k_full[st], C::kKBytes);
                 uint8_t* sk = smem + C::kOffKV + st * C::kStage;
-                uint8_t* sv = sk + C::kKBytes;
                 const int key = k_begin + j * C::BN;
-                for (int a = 0; a < C::ATOMS; ++a) {
-                    tma_load_2d(sk + a * C::kAtomKV, &tm_k, &kv_full[st], hk * DH + a * 64, key, kEvictFirst);
-                    tma_load_2d(sv + a * C::kAtomKV, &tm_v, &kv_full[st], hk * DH + a * 64, key, kEvictFirst);
-                }
+                for (int a = 0; a < C::ATOMS; ++a)
+                    tma_load_2d(sk + a * C::kAtomKV, &tm_k, &k_full[st], hk * DH + a * 64, key, kEvictFirst);
+            }
+        }
+    } else if (warp == 3) {
+        // V producer
+        if (elect_one() && ntiles > 0) {
+            for (int j = 0; j < ntiles; ++j) {
+                const int st = j & 1;
+                mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&v_full[st], C::kKBytes);
+                uint8_t* sv = smem + C::kOffKV + st * C::kStage + C::kKBytes;
+                const int key = k_begin + j * C::BN;
+                for (int a = 0; a < C::ATOMS; ++a)
+                    tma_load_2d(sv + a * C::kAtomKV, &tm_v, &v_full[st], hk * DH + a * 64, key, kEvictFirst);
             }
         }
     } else if (warp == 1) {
@@ -114,7 +128,7 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
             mbar_wait(q_full, 0);
             auto issue_qk = [&](int j) {
                 const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                mbar_wait(&k_full[st], (j >> 1) & 1);
                 mbar_wait(&s_empty[st], ((j >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint8_t* sk = smem + C::kOffKV + st * C::kStage;
@@ -125,10 +139,12 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
                     const uint64_t b = umma_desc_k_sw128(smem_u32(sk + (kk >> 2) * C::kAtomKV)) + 2 * (kk & 3);
                     umma_f16(d, a, b, idesc_qk, kk != 0);
                 }
+                umma_commit(&k_empty[st]);
                 umma_commit(&s_full[st]);
             };
             auto issue_pv = [&](int j) {
                 const int st = j & 1;
+                mbar_wait(&v_full[st], (j >> 1) & 1);
                 mbar_wait(&p_full[st], (j >> 1) & 1);
                 tc_fence_after();
                 const uint8_t* sv = smem + C::kOffKV + st * C::kStage + C::kKBytes;
@@ -141,7 +157,7 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
                     const uint64_t b = umma_desc_mn_sw128(smem_u32(sv + kk * 16 * 128), C::kAtomKV, 1024);
                     umma_f16(d, a, b, idesc_pv, (j | kk) != 0);
                 }
-                umma_commit(&kv_empty[st]);
+                umma_commit(&v_empty[st]);
                 umma_commit(&p_empty[st]);
             };
             issue_qk(0);

@@ -13,6 +13,9 @@ ACT_NONE, ACT_GELU_ERF, ACT_GELU_TANH, ACT_SOFTCAP, ACT_SILU = 0, 1, 2, 3, 4
 GLU_NONE, GLU_GELU_TANH, GLU_SILU = 0, 1, 2
 BF16 = torch.bfloat16
 
+# CTA-pair (cta_group::2) GEMM for large-M problems; flipped on once it beats the 1-CTA kernel on the box
+USE_2CTA = True
+
 # bench instrumentation: when PROFILE is a list, every gemm() appends (tag, algorithmic_flops, start_evt, end_evt)
 PROFILE = None
 
@@ -48,7 +51,7 @@ def pick_block_n(M: int, N: int, glu: bool = False) -> int:
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          res_mod: int = 0, act: int = ACT_NONE, act_param: float = 0.0, out: Optional[torch.Tensor] = None,
          out_fp32: bool = False, glu: int = GLU_NONE, block_n: Optional[int] = None, tag: str = "gemm",
-         alg_k: Optional[int] = None) -> torch.Tensor:
+         alg_k: Optional[int] = None, cta2: Optional[bool] = None) -> torch.Tensor:
     """out[M,N(/2)] = epi(a[M,K] @ w[N,K]^T).  a,w bf16; bias fp32.
     tag / alg_k only feed the bench's roofline accounting (alg_k = un-padded contraction length)."""
     L = _lib.load()
@@ -72,7 +75,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = L.vidi_gemm_bf16(_ptr(a), _rowmajor(a), _ptr(w), _rowmajor(w), _ptr(out), _rowmajor(out), M, N, K,
+    if cta2 is None:
+        cta2 = USE_2CTA and M >= 1024 and block_n in (128, 192, 256)
+    fn = L.vidi_gemm_bf16_2cta if cta2 else L.vidi_gemm_bf16
+    rc = fn(_ptr(a), _rowmajor(a), _ptr(w), _rowmajor(w), _ptr(out), _rowmajor(out), M, N, K,
                           _ptr(bias), _ptr(residual), _rowmajor(residual) if residual is not None else 0, res_mod,
                           act, act_param, 1 if out.dtype == torch.float32 else 0, glu, block_n, _stream())
     _lib.check(rc, "gemm_bf16")
