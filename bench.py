@@ -186,6 +186,8 @@ def run_ours(args):
     from vidi_b200.engine import make_plan
     from vidi_b200.model import DattnGemma2ForCausalLM
 
+    if args.gemm != "auto":
+        ops.USE_2CTA = args.gemm == "2cta"
     cfg = vidi15_9b()
     F, Cn, T, label = WORKLOADS[args.workload]
     t0 = time.time()
@@ -299,7 +301,8 @@ def run_ours(args):
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=round(e2e_v, 1), unit=UNIT, ms_per_step=round(ms_e2e / args.steps, 2), h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors"),
-                gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1))
+                gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
+                gemm_variant="2cta (cta_group::2) for M>=1024, 1cta otherwise" if ops.USE_2CTA else "1cta")
     print(json.dumps(line), flush=True)
 
 
@@ -311,6 +314,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default="auto", choices=["auto", "1cta", "2cta"], help="A/B switch for the CTA-pair GEMM")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, no e2e / cpu legs (for ncu launch lists; not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,9 +4,12 @@ Same rules as vidi15_ref.py (only tests / smoke / bench cpu legs may import it).
 Vidi_7B/model/lmm/dattn/mistral.py:44-116 (forward_xattn), :131-137 (feed_foward), :139-274 (decoder layer),
 :296-453 (model loop), :596-616 (lm_head, fp32 logits), Vidi_7B/model/lmm/dattn/multimodal.py:154-227 (encoders)
 and Vidi_7B/model/mm_vision/pool.py:6-26 (learned conv pool + align_corners bilinear).
-PARITY PINNING: the leaf pool module is pinned by tests/golden (reference Conv2DPool run by file path); the
-Mistral decoder layer is "parity unpinned" -- the reference subclasses transformers==4.44.2's
-MistralFlashAttention2, which the installed transformers 5.5.0 no longer ships, so it cannot be run here.
+PARITY PINNING (tests/test_oracle_golden.py): the learned-conv pool is checked against the reference's Conv2DPool
+run by file path, and ``stream_layer`` + ``text_layer`` against two stacked calls of the reference's own
+DattnMistralDecoderLayer.forward / forward_xattn / flash_cross_attention_forward (tests/golden/make_golden_7b.py;
+the transformers==4.44.2 MistralFlashAttention2 base class, gone from the installed 5.5.0, and flash-attn's kernels are
+replaced there by fp32 restatements of their semantics) to <= 5e-5.  Unpinned: the encoders' composition
+(multimodal.py:154-227, restated from source; its leaf modules are pinned) and the model-level loop / lm_head.
 Differences from Vidi1.5: no sqrt(D) normaliser, Mistral RMSNorm (w * x_hat, eps from config), one
 MLP norm (= post_attention_layernorm), SwiGLU, no soft-caps, scale 1/sqrt(128), diagonal update without a norm,
 residual added after summing the three attentions, learned-conv pooling to pool^2 tokens per frame, audio pool keeps

@@ -88,3 +88,15 @@ def install():
 if __name__ == "__main__":
     G, X = install()
     print("reference modules imported:", G.__file__)
+
+
+def eager_flash_attn_varlen_func(q, k, v, cu_seqlens_q=None, cu_seqlens_k=None, max_seqlen_q=None, max_seqlen_k=None,
+                                 dropout_p=0.0, softmax_scale=None, causal=False, softcap=0.0, deterministic=False, **kw):
+    """flash_attn_varlen_func semantics: packed q [Tq,H,D], k/v [Tk,Hk,D], per-sequence boundaries in cu_seqlens_*."""
+    outs = []
+    for b in range(len(cu_seqlens_q) - 1):
+        qs, qe = int(cu_seqlens_q[b]), int(cu_seqlens_q[b + 1])
+        ks, ke = int(cu_seqlens_k[b]), int(cu_seqlens_k[b + 1])
+        outs.append(eager_flash_attn_func(q[None, qs:qe], k[None, ks:ke], v[None, ks:ke], softmax_scale=softmax_scale,
+                                          causal=causal, softcap=softcap)[0])
+    return torch.cat(outs, 0)

@@ -144,3 +144,37 @@ def test_vidi7b_prefill_mini():
     top2 = ref.topk(2, -1).values
     confident = (top2[:, 0] - top2[:, 1]) > 2 * err
     assert torch.equal(logits.cpu().argmax(-1)[confident], ref.argmax(-1)[confident])
+
+
+def test_facade_forward_generate_match_oracle():
+    """Drop-in surface (model.py): forward(..., images=, audios=, audio_sizes=) logits and greedy generate() ids vs the oracle,
+    including the decode steps that run q_len=1 against the cached image/audio/text K,V (gemma.py:64-65,603-655)."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_mini
+    from vidi_b200.model import DattnGemma2ForCausalLM, IMAGE_TOKEN_INDEX
+    cfg = vidi15_mini()
+    sd = {k: (v if "mm_rand_pos" in k else v.to(BF).float()) for k, v in synth.make_state_dict(cfg, seed=99).items()}
+    model = DattnGemma2ForCausalLM(cfg, {k: v.clone() for k, v in sd.items()}, device="cuda")
+    ids, images, mels, asz = synth.make_inputs(cfg, 4, 1, n_text=14, seed=5)
+    images = images.to(BF).float(); mels = mels.to(BF).float()
+    assert int((ids == IMAGE_TOKEN_INDEX).sum()) == 1
+    out = model(ids[None], images=images[None], audios=mels[None], audio_sizes=[asz])       # host fp32 inputs, no mask
+    ref = R.prefill(sd, cfg, ids, images, mels, asz, normalizer_dtype=BF)
+    assert out.logits.shape == (1, 14, cfg.llm.vocab)
+    assert rel(out.logits[0], ref) < 3e-2
+    k_img, v_img = out.past_image_key_values[0]
+    assert k_img.shape == (1, cfg.image_tokens(4), cfg.llm.kv_dim) and len(out.past_image_key_values) == cfg.llm.layers
+    assert out.past_audio_key_values[0][0].shape[1] == cfg.audio_tokens(asz)
+    # greedy decode: compare step by step while the oracle's margin is decisive
+    n_new = 6
+    gen = model.generate(ids[None], images=images[None], audios=mels[None], audio_sizes=[asz], do_sample=False,
+                         max_new_tokens=n_new, use_cache=True, disable_compile=True, pad_token_id=0)
+    ref_ids = R.greedy_generate(sd, cfg, ids, images, mels, asz, max_new_tokens=n_new, normalizer_dtype=BF)
+    assert gen.shape[0] == 1 and gen.shape[1] <= n_new
+    g = gen[0].tolist()
+    assert g[0] == ref_ids[0]
+    assert g[:len(ref_ids)] == ref_ids[:len(g)] or sum(a == b for a, b in zip(g, ref_ids)) >= len(ref_ids) - 1
+    with pytest.raises(NotImplementedError):
+        model.generate(ids[None], inputs_embeds=torch.zeros(1))
+    with pytest.raises(ValueError):
+        model.forward(None)

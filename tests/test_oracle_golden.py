@@ -115,3 +115,24 @@ def test_vidi7b_oracle_runs_and_shapes():
     ids, images, mels, asz = synth.make_inputs(cfg, 2, 1, n_text=7, audio_size=900)
     logits = R7.prefill(sd, cfg, ids, images, mels, asz)
     assert logits.shape == (7, cfg.llm.vocab) and torch.isfinite(logits).all()
+
+
+def test_vidi7b_decoder_layers_match_reference_layer_forward():
+    """oracle/vidi7b_ref.py stream_layer + text_layer vs the reference's own DattnMistralDecoderLayer.forward
+    (tests/golden/make_golden_7b.py: two stacked layers, all three streams, varlen cross-attention path)."""
+    from oracle import vidi7b_ref as R7
+    from vidi_b200.config import MistralCfg, Vidi7BConfig
+    G7 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vidi7b_reference_golden.pt"), weights_only=False)
+    c = G7["cfg"]
+    cfg = Vidi7BConfig(llm=MistralCfg(**c["llm"]), vis=VisionCfg(**c["vis"]), aud=AudioCfg(**c["aud"]), mm_image_pool_size=c["pool"])
+    sd = synth.make_state_dict(cfg, seed=G7["seed"])
+    H, S_img, S_aud = G7["H0"], G7["img0"], G7["aud0"]
+    cos, sin = R.rope_cos_sin(H.shape[0], cfg.llm.head_dim, cfg.llm.rope_theta)
+    ones_i, ones_a = torch.ones(S_img.shape[0], dtype=torch.bool), torch.ones(S_aud.shape[0], dtype=torch.bool)
+    for l, ref in enumerate(G7["layers"]):
+        p = f"model.layers.{l}"
+        S_img2, Ki, Vi = R7.stream_layer(S_img, sd, p, cfg)
+        S_aud2, Ka, Va = R7.stream_layer(S_aud, sd, p, cfg)
+        H = R7.text_layer(H, sd, p, cfg, cos, sin, [(Ki, Vi, ones_i), (Ka, Va, ones_a)])
+        S_img, S_aud = S_img2, S_aud2
+        close(S_img, ref["image"], 5e-5); close(S_aud, ref["audio"], 5e-5); close(H, ref["text"], 5e-5)

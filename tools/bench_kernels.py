@@ -97,6 +97,9 @@ if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[1] == "one"):
         gemm_case("vit_fc2", 64 * 729, 1152, 4304)
         gemm_case("vit_out", 64 * 729, 1152, 1152)
         gemm_case("square8k", 8192, 8192, 8192)
+        gemm_case("kv_proj_M126k", 126000, 4096, 3584)
+        gemm_case("gate_up_M126k", 126000, 28672, 3584, glu=1)
+        gemm_case("down_M126k", 126000, 3584, 14336)
         gemm_case("text_gateup", 32, 28672, 3584, glu=1)
         gemm_case("text_down", 32, 3584, 14336)
         gemm_case("text_down_bn64", 32, 3584, 14336, bn=64)

@@ -209,20 +209,24 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_
                 tc_fence_before();
                 mbar_arrive(&s_empty[st]);                             // S is in registers now
                 const int kbase = j * C::BN + wg * 64;
+                // running max on the RAW scores (scale > 0 is monotone); the scale is folded into the exp2 FMA below
+                if (kbase + 64 > p.S) {                                // only the last key tile can be ragged
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (kbase + i >= p.S) r0[i] = 0xff800000u;     // -inf
+                        if (kbase + 32 + i >= p.S) r1[i] = 0xff800000u;
+                    }
+                }
                 float mx = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float a = __uint_as_float(r0[i]) * p.scale_log2, c = __uint_as_float(r1[i]) * p.scale_log2;
-                    if (kbase + i >= p.S) a = -INFINITY;
-                    if (kbase + 32 + i >= p.S) c = -INFINITY;
-                    r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(c);
-                    mx = fmaxf(mx, fmaxf(a, c));
-                }
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
                 xmax[st][wg][row] = mx;
                 asm volatile("bar.sync 1, 256;" ::: "memory");         // softmax warps only
                 const float m_new = fmaxf(m, fmaxf(mx, xmax[st][wg ^ 1][row]));
-                const float corr = exp2f(m - m_new);                   // first tile: exp2(-inf) = 0
+                float corr;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"((m - m_new) * p.scale_log2));   // first tile: 2^-inf = 0
                 m = m_new;
+                const float neg_m = -m_new * p.scale_log2;
                 mbar_wait(&p_empty[st], ph ^ 1);
                 uint8_t* sp = smem + C::kOffP + st * C::kPBytes + wg * C::kMainBytes + row * 128;
                 float rs = 0.f;
@@ -233,7 +237,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid_
                     for (int e = 0; e < 8; ++e) {
                         const int i = c8 * 8 + e;
                         const float sv = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-                        pv[e] = exp2f(sv - m);
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(sv, p.scale_log2, neg_m)));
                         rs += pv[e];
                     }
                     const uint4 q = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),

@@ -94,6 +94,9 @@ class Vidi15Engine:
         # torch.tensor(hidden**0.5, dtype=act): the normaliser is rounded to the activation dtype (gemma.py:353); Mistral has none
         self.normalizer = float(torch.tensor(cfg.llm.hidden ** 0.5, dtype=BF16).float()) if self.gemma else 1.0
         self.glu = ops.GLU_GELU_TANH if self.gemma else ops.GLU_SILU
+        # GEMM variant per site, from same-box A/B runs of the full step (profiles/): the CTA-pair kernel wins on the tower /
+        # projector shapes (K=1152..5120), the 1-CTA kernel sustains more on the long stream-pass GEMMs at M ~ 1e5.
+        self.llm_cta2 = False
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
@@ -222,16 +225,16 @@ class Vidi15Engine:
         y = torch.empty_like(S)
         g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
-            ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv")
+            ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv", cta2=self.llm_cta2)
             if l == len(Ls) - 1:
                 break
-            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo")
+            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo", cta2=self.llm_cta2)
             if gm:      # S += G(y, w_post); h = G(S, w_preff)          (gemma.py:198-202,116-118)
                 ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
             else:       # S += y; h = norm(S, w_post_attention)          (mistral.py:223-225,131-133)
                 ops.residual_norm(S, y, None, L.n_post, h, c.rms_eps, 0, False)
-            ops.gemm(h, L.wgu, glu=self.glu, out=g, tag="llm_gateup")
-            ops.gemm(g, L.wd, out=y, tag="llm_down")
+            ops.gemm(h, L.wgu, glu=self.glu, out=g, tag="llm_gateup", cta2=self.llm_cta2)
+            ops.gemm(g, L.wd, out=y, tag="llm_down", cta2=self.llm_cta2)
             if gm:
                 ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
             else:
