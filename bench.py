@@ -204,16 +204,17 @@ def run_ours(args):
     plan = make_plan(cfg, F, Cn, asz, rank, world)
     ids = torch.randint(3, cfg.llm.vocab, (1, T + 1), generator=g); ids[0, 0] = 2; ids[0, 1] = -200
     g_dev = torch.Generator(device=dev); g_dev.manual_seed(4321)
-    # every rank holds the full host tensors (as the reference replicates inputs inside an SP group); only its shard moves
-    host_img = torch.empty(1, F, 3, 384, 384, dtype=torch.bfloat16).pin_memory()
+    # each rank pins only its contiguous shard of frames / chunks on the host (mm_total mode of the facade)
+    fl = plan.f1 - plan.f0
+    host_img = torch.empty(1, fl, 3, 384, 384, dtype=torch.bfloat16).pin_memory()
     chunk = 256
-    for s in range(0, F, chunk):
-        e = min(F, s + chunk)
-        gi = torch.Generator(device=dev); gi.manual_seed(4321 + s)
+    for s in range(0, fl, chunk):
+        e = min(fl, s + chunk)
+        gi = torch.Generator(device=dev); gi.manual_seed(4321 + plan.f0 + s)
         host_img[0, s:e].copy_(torch.randn(e - s, 3, 384, 384, generator=gi, device=dev).clamp_(-1, 1).to(torch.bfloat16))
-    host_mel = (0.5 * torch.randn(1, Cn, 128, 3000, generator=g)).to(torch.bfloat16).pin_memory()
-    dev_img = host_img[0, plan.f0:plan.f1].to(dev)
-    dev_mel = host_mel[0, plan.c0:plan.c1].to(dev)
+    host_mel = (0.5 * torch.randn(1, Cn, 128, 3000, generator=g))[:, plan.c0:plan.c1].to(torch.bfloat16).contiguous().pin_memory()
+    dev_img = host_img[0].to(dev)
+    dev_mel = host_mel[0].to(dev)
     ids_dev = ids[0][ids[0] != -200].to(dev)
     n_tokens = plan.n_img_total + plan.n_aud_total + T
 
@@ -221,7 +222,7 @@ def run_ours(args):
         return eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, logits_to_keep=0)
 
     def step_e2e():
-        out = model.forward(ids, images=host_img, audios=host_mel, audio_sizes=[asz])
+        out = model.forward(ids, images=host_img, audios=host_mel, audio_sizes=[asz], mm_total=(F, Cn))
         return out.logits[0, -1].float().cpu()                       # device->host read of the step's result
 
     def barrier():
@@ -234,6 +235,7 @@ def run_ours(args):
         ops.reset_launch_count()
         if profile:
             ops.PROFILE = []
+            ops.PROFILE_OPS = {}
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
@@ -243,6 +245,9 @@ def run_ours(args):
         ms = s.elapsed_time(e)
         launches = ops.launch_count()
         prof, ops.PROFILE = ops.PROFILE, None
+        prof_ops, ops.PROFILE_OPS = ops.PROFILE_OPS, None
+        if profile:
+            timed.by_op = {k: (round(sum(a.elapsed_time(b) for a, b in v) / steps, 3), len(v) // steps) for k, v in (prof_ops or {}).items()}
         if world > 1:
             t = torch.tensor([ms], device=dev)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -301,6 +306,7 @@ def run_ours(args):
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=round(e2e_v, 1), unit=UNIT, ms_per_step=round(ms_e2e / args.steps, 2), h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors"),
+                other_ops_ms_per_step={k: v[0] for k, v in sorted(getattr(timed, "by_op", {}).items(), key=lambda kv: -kv[1][0])},
                 gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
                 gemm_variant="2cta (cta_group::2) for M>=1024, 1cta otherwise" if ops.USE_2CTA else "1cta")
     print(json.dumps(line), flush=True)

@@ -85,6 +85,9 @@ int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 /* bidirectional flash attention for the towers (flash_attn_func via HF SiglipAttention / WhisperAttention), K3/K8 */
 int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,
                     int dh, float scale, void* stream);
+/* same contract, first-generation tcgen05 kernel (one query block per item, split-key softmax warpgroups); A/B bar */
+int vidi_attn_dense_v1(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
+                       int H, int dh, float scale, void* stream);
 /* same contract, always the warp-level mma.sync kernel (generic strides / head dims; kept as the A/B bar for the tcgen05 path) */
 int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                         int H, int dh, float scale, void* stream);

@@ -178,3 +178,49 @@ def test_facade_forward_generate_match_oracle():
         model.generate(ids[None], inputs_embeds=torch.zeros(1))
     with pytest.raises(ValueError):
         model.forward(None)
+
+
+def test_prefill_long_text_multiple_query_blocks():
+    """T = 150 text tokens -> 300 virtual rows = 3 query blocks in the cross-attention kernel, text attention over 150 keys."""
+    from vidi_b200.config import vidi15_mini
+    run_case(vidi15_mini(), n_frames=2, n_chunks=1, n_text=150, audio_size=300, check_stages=False)
+
+
+def test_prefill_single_modality():
+    """images only / audios only (encode_videos handles either being None, multimodal.py:254-265)."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_mini
+    cfg = vidi15_mini()
+    sd, eng = build(cfg)
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=10, audio_size=700)
+    images = images.to(BF).float(); mels = mels.to(BF).float()
+    ids_dev = R.strip_image_token(ids).cuda()
+    ref_i = R.prefill(sd, cfg, ids, images, None, None, normalizer_dtype=BF)
+    out_i = eng.prefill(ids_dev, images.cuda().to(BF), None, 0)
+    assert rel(out_i, ref_i) < 3e-2
+    ref_a = R.prefill(sd, cfg, ids, None, mels, asz, normalizer_dtype=BF)
+    out_a = eng.prefill(ids_dev, None, mels.cuda().to(BF), asz)
+    assert rel(out_a, ref_a) < 3e-2
+
+
+def test_facade_batch_with_padding_mask():
+    """B=2 with right padding + attention_mask: each sample is stripped of padding and the sentinel (multimodal.py:363-397)."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_mini
+    from vidi_b200.model import DattnGemma2ForCausalLM
+    cfg = vidi15_mini()
+    sd = {k: (v if "mm_rand_pos" in k else v.to(BF).float()) for k, v in synth.make_state_dict(cfg, seed=11).items()}
+    model = DattnGemma2ForCausalLM(cfg, {k: v.clone() for k, v in sd.items()}, device="cuda")
+    ids0, img0, mel0, a0 = synth.make_inputs(cfg, 2, 1, n_text=9, seed=1, audio_size=500)
+    ids1, img1, mel1, a1 = synth.make_inputs(cfg, 2, 1, n_text=5, seed=2, audio_size=900)
+    img0, img1, mel0, mel1 = [t.to(BF).float() for t in (img0, img1, mel0, mel1)]
+    L = max(ids0.numel(), ids1.numel())
+    ids = torch.zeros(2, L, dtype=torch.long); mask = torch.zeros(2, L, dtype=torch.long)
+    ids[0, :ids0.numel()] = ids0; mask[0, :ids0.numel()] = 1
+    ids[1, :ids1.numel()] = ids1; mask[1, :ids1.numel()] = 1
+    out = model(ids, attention_mask=mask, images=torch.stack([img0, img1]), audios=torch.stack([mel0, mel1]), audio_sizes=[a0, a1])
+    r0 = R.prefill(sd, cfg, ids0, img0, mel0, a0, normalizer_dtype=BF)
+    r1 = R.prefill(sd, cfg, ids1, img1, mel1, a1, normalizer_dtype=BF)
+    assert out.logits.shape == (2, 9, cfg.llm.vocab)
+    assert rel(out.logits[0], r0) < 3e-2 and rel(out.logits[1, :5], r1) < 3e-2
+    assert float(out.logits[1, 5:].abs().max()) == 0.0

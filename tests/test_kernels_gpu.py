@@ -250,7 +250,7 @@ def test_embed_gather_and_pos_split():
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("impl", ["auto", "mma"])
+@pytest.mark.parametrize("impl", ["auto", "v1", "mma"])
 @pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (1, 100, 2, 72), (2, 64, 2, 64), (5, 729, 16, 72),
                                       (1, 129, 1, 72), (3, 257, 3, 64)])
 def test_attn_dense(B, S, H, dh, impl):

@@ -64,7 +64,8 @@ def dense_case(B, S, H, dh):
     t = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out))
     fl = 4.0 * B * H * S * S * dh
     t_m = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="mma"))
-    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), mma_ms=round(t_m, 4),
+    t_1 = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="v1"))
+    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), v1_tflops=round(fl / t_1 / 1e9, 1), mma_ms=round(t_m, 4),
                mma_tflops=round(fl / t_m / 1e9, 1))
     try:
         from flash_attn import flash_attn_func

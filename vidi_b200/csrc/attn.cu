@@ -365,30 +365,51 @@ xattn_splitkv_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __n
 // Partial p = (rank r = p / spr, split s = p % spr) lives at Opart + r*rank_stride_o + s*rows*DH and
 // LSE + r*rank_stride_l + s*rows, so the buffer produced by one all-gather of every rank's flat
 // [O | LSE] block can be merged in place (spr = splits per rank).
-__global__ void xattn_merge_kernel(const float* __restrict__ Opart, const float* __restrict__ LSE, int P, int spr,
-                                   int64_t rank_stride_o, int64_t rank_stride_l, int rows, int DH, float gate,
-                                   int accumulate, float* __restrict__ out) {
+__global__ void __launch_bounds__(128)
+xattn_merge_kernel(const float* __restrict__ Opart, const float* __restrict__ LSE, int P, int spr,
+                   int64_t rank_stride_o, int64_t rank_stride_l, int rows, int DH, float gate,
+                   int accumulate, float* __restrict__ out) {
     const int row = blockIdx.x;
-    extern __shared__ float wts[];                 // [P]
-    float L = -INFINITY;
-    for (int p = 0; p < P; ++p) L = fmaxf(L, LSE[(p / spr) * rank_stride_l + (int64_t)(p % spr) * rows + row]);
-    float denom = 0.f;
-    for (int p = 0; p < P; ++p) {
+    extern __shared__ float wts[];                 // [P] weights, then 4 floats of reduction scratch
+    __shared__ float red[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // phase 1: every partial's LSE is read once (thread-parallel over p), block max
+    float lmax = -INFINITY;
+    for (int p = tid; p < P; p += 128) {
         const float l = LSE[(p / spr) * rank_stride_l + (int64_t)(p % spr) * rows + row];
-        const float w = (l == -INFINITY) ? 0.f : __expf(l - L);
-        denom += w;
-        if (threadIdx.x == 0) wts[p] = w;
+        wts[p] = l;
+        lmax = fmaxf(lmax, l);
     }
+    lmax = warp_max(lmax);
+    if (lane == 0) red[warp] = lmax;
     __syncthreads();
+    const float L = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    // phase 2: weights + denominator
+    float dsum = 0.f;
+    for (int p = tid; p < P; p += 128) {
+        const float l = wts[p];
+        const float w = (l == -INFINITY) ? 0.f : __expf(l - L);
+        wts[p] = w;
+        dsum += w;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) red[warp] = dsum;
+    __syncthreads();
+    const float denom = red[0] + red[1] + red[2] + red[3];
     const float invd = denom > 0.f ? gate / denom : 0.f;
-    for (int c = threadIdx.x; c < DH; c += blockDim.x) {
-        float acc = 0.f;
+    // phase 3: weighted sum of the partial rows, float2 per thread (DH = 256 -> one pass, DH = 128 -> half the threads)
+    for (int c = tid * 2; c < DH; c += 256) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 4
         for (int p = 0; p < P; ++p) {
             const float w = wts[p];
-            if (w != 0.f) acc += w * Opart[(p / spr) * rank_stride_o + ((int64_t)(p % spr) * rows + row) * DH + c];
+            const float2 v = *reinterpret_cast<const float2*>(Opart + (p / spr) * rank_stride_o + ((int64_t)(p % spr) * rows + row) * DH + c);
+            acc.x += w * v.x; acc.y += w * v.y;
         }
-        float* o = out + (int64_t)row * DH + c;
-        *o = (accumulate ? *o : 0.f) + acc * invd;
+        float2* o = reinterpret_cast<float2*>(out + (int64_t)row * DH + c);
+        float2 prev = accumulate ? *o : make_float2(0.f, 0.f);
+        *o = make_float2(prev.x + acc.x * invd, prev.y + acc.y * invd);
     }
 }
 

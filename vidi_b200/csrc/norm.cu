@@ -149,6 +149,7 @@ residual_norm_kernel(__nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bflo
 // ------------------------------------------------------------------------------------------------
 // LayerNorm with affine (towers): y = (x - mean) * rsqrt(var + eps) * w + b ; w,b fp32
 // ------------------------------------------------------------------------------------------------
+template <int kVec>
 __global__ void __launch_bounds__(kRowWarps * 32)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                  const float* __restrict__ b, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int D, float eps) {
@@ -157,10 +158,10 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* 
     const int lane = lane_id();
     const int nvec = D >> 3;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
-    uint4 cache[kMaxVec];
+    uint4 cache[kVec];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
             cache[i] = ld_stream(xr + v);
@@ -172,7 +173,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* 
     const float mean = warp_sum(s) / (float)D;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
             float f[8]; unpack8(cache[i], f);
@@ -183,7 +184,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* 
     const float inv = rsqrtf(warp_sum(ss) / (float)D + eps);
     uint4* yr = reinterpret_cast<uint4*>(y + (int64_t)row * ldy);
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
         const int v = lane + i * 32;
         if (v < nvec) {
             float f[8]; unpack8(cache[i], f);
@@ -356,8 +357,11 @@ int layernorm(const void* x, int64_t ldx, const float* w, const float* b, void* 
               float eps, cudaStream_t st) {
     VB_REQUIRE(D % 8 == 0 && D <= kMaxVec * 256 && ldx % 8 == 0 && ldy % 8 == 0, "layernorm: D=%d unsupported", D);
     if (rows == 0) return 0;
-    layernorm_kernel<<<row_grid(rows), kRowWarps * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, w, b, (__nv_bfloat16*)y,
-                                                                 ldy, rows, D, eps);
+    // per-lane cache sized to the row width: fewer registers -> more rows in flight per SM for the 1152 / 1280-wide towers
+    const int vec = (D / 8 + 31) / 32;
+#define VB_LN(V) layernorm_kernel<V><<<row_grid(rows), kRowWarps * 32, 0, st>>>((const __nv_bfloat16*)x, ldx, w, b, (__nv_bfloat16*)y, ldy, rows, D, eps)
+    if (vec <= 2) VB_LN(2); else if (vec <= 5) VB_LN(5); else if (vec <= 8) VB_LN(8); else VB_LN(16);
+#undef VB_LN
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

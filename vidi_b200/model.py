@@ -125,21 +125,34 @@ class DattnGemma2ForCausalLM:
         assert n_img <= 1, "only support at most one image for now."      # multimodal.py:369
         return ids_row[ids_row != IMAGE_TOKEN_INDEX]
 
-    def _prefill_one(self, ids, images, audios, audio_size, max_len, logits_to_keep):
+    def _prefill_one(self, ids, images, audios, audio_size, max_len, logits_to_keep, mm_total=None):
+        """mm_total=(F_total, C_total): `images` / `audios` already hold only THIS RANK's contiguous shard of frames /
+        chunks (engine.make_plan) -- the host-memory-friendly multi-GPU mode; otherwise they are the full tensors and
+        the shard is sliced here (the reference replicates inputs inside an SP group, vidi_trainer.py:222-254)."""
         eng = self.engine
         img = aud = None
         F = Cn = 0
         iv = av = True
-        if images is not None:
-            F = images.shape[0]
-            plan = make_plan(self.cfg, F, audios.shape[0] if audios is not None else 0, audio_size or 0, eng.rank, eng.world)
-            img = self._dev(images[plan.f0:plan.f1])
-            iv = self._any_nonzero(img)                                  # multimodal.py:202 (input validity, not compute)
-        if audios is not None:
-            Cn = audios.shape[0]
+        if mm_total is not None:
+            F, Cn = int(mm_total[0]), int(mm_total[1])
             plan = make_plan(self.cfg, F, Cn, audio_size or 0, eng.rank, eng.world)
-            aud = self._dev(audios[plan.c0:plan.c1])
-            av = self._any_nonzero(aud)
+            if images is not None:
+                assert images.shape[0] == plan.f1 - plan.f0, "images must be this rank's frame shard"
+                img = self._dev(images); iv = self._any_nonzero(img)
+            if audios is not None:
+                assert audios.shape[0] == plan.c1 - plan.c0, "audios must be this rank's chunk shard"
+                aud = self._dev(audios); av = self._any_nonzero(aud)
+        else:
+            if images is not None:
+                F = images.shape[0]
+                plan = make_plan(self.cfg, F, audios.shape[0] if audios is not None else 0, audio_size or 0, eng.rank, eng.world)
+                img = self._dev(images[plan.f0:plan.f1])
+                iv = self._any_nonzero(img)                              # multimodal.py:202 (input validity, not compute)
+            if audios is not None:
+                Cn = audios.shape[0]
+                plan = make_plan(self.cfg, F, Cn, audio_size or 0, eng.rank, eng.world)
+                aud = self._dev(audios[plan.c0:plan.c1])
+                av = self._any_nonzero(aud)
         tc = eng.new_text_cache(max_len)
         ids_dev = ids.to(self.device, dtype=torch.int64).contiguous()
         logits, st = eng.prefill(ids_dev, img, aud, audio_size or 0, n_frames_total=F, n_chunks_total=Cn,
@@ -170,7 +183,7 @@ class DattnGemma2ForCausalLM:
             img = images[b] if images is not None else None
             aud = audios[b] if audios is not None else None
             asz = int(audio_sizes[b]) if audio_sizes is not None else (aud.shape[0] * self.cfg.aud.nb_max_frames if aud is not None else 0)
-            lg, st = self._prefill_one(ids, img, aud, asz, ids.numel() + 1, logits_to_keep)
+            lg, st = self._prefill_one(ids, img, aud, asz, ids.numel() + 1, logits_to_keep, mm_total=kw.get("mm_total"))
             outs.append(lg); states.append(st)
         T = max(o.shape[0] for o in outs)
         logits = torch.zeros(B, T, outs[0].shape[1], device=self.device, dtype=torch.float32)

@@ -247,18 +247,19 @@ def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None, imp
     assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
     if out is None:
         out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
-    fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense
+    fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense_v1 if impl == "v1" else L.vidi_attn_dense
     _lib.check(fn(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale, _stream()),
                "attn_dense")
     return out
 
 
 def xattn_splits(n_keys: int, hkv: int, n_sms: int = 148) -> int:
-    """number of key splits so that splits*hkv CTAs cover the SMs ~2x, with >= 256 keys per split."""
+    """number of key splits so that splits*hkv CTAs fill the SMs once (one persistent-style wave), >= 512 keys per split.
+    Fewer, longer splits amortise the per-CTA prologue and keep the (O, LSE) partial set small for the merge."""
     if n_keys <= 0:
         return 1
-    want = max(1, (2 * n_sms) // max(hkv, 1))
-    return max(1, min(want, (n_keys + 255) // 256))
+    want = max(1, n_sms // max(hkv, 1))
+    return max(1, min(want, (n_keys + 511) // 512))
 
 
 def xattn_splitkv(q, k, v, kmask, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, splits: int,
@@ -320,3 +321,33 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     _lib.load().vidi_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench instrumentation for the non-GEMM ops: when PROFILE_OPS is a dict, every wrapped op accumulates
+# (calls, [event pairs]) under its name.  Zero overhead when PROFILE_OPS is None.
+# ------------------------------------------------------------------------------------------------------
+PROFILE_OPS = None
+
+
+def _instrument(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        prof = PROFILE_OPS
+        if prof is None:
+            return fn(*a, **k)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        prof.setdefault(fn.__name__, []).append((e0, e1))
+        return r
+    return wrapped
+
+
+for _name in ("rmsnorm", "residual_norm", "layernorm", "mm_finish", "rmsnorm_f32", "patch_im2col", "whisper_im2col1",
+              "whisper_im2col2", "pool_s2d", "conv_window_gather", "bilinear_ac", "embed_gather", "sinusoid_split", "split3",
+              "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text"):
+    globals()[_name] = _instrument(globals()[_name])
