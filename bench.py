@@ -34,6 +34,8 @@ WORKLOADS = {
     "c2p": (600, 20, 32, "Vidi1.5-9B 10-min synthetic video, 66k tokens (BASELINE config 2')"),
     "c2": (80, 3, 32, "Vidi1.5-9B 80-frame synthetic video, 16.5k tokens (BASELINE config 2)"),
     "c1": (8, 1, 32, "Vidi1.5-9B 8-frame plumbing case (BASELINE config 1)"),
+    # Vidi-7B: per clip 300 frames / 10 chunks; a step = 8 clips back to back (BASELINE config 4, mm_image_pool_size=16 assumed)
+    "c4": (300, 10, 32, "Vidi-7B batch 8 x 5-min synthetic clips, 8 x (76.8k image + 3k audio) tokens (BASELINE config 4)"),
 }
 METRIC = "prefill multimodal-tokens/sec, Vidi1.5-9B @128k seq"
 UNIT = "tokens/s"
@@ -99,6 +101,20 @@ def dist_env():
 # reference arm / cpu_baseline: the fp32 oracle on the host cores, on a bounded sample, extrapolated
 # =====================================================================================================
 def cpu_sample(workload: str, budget_scale: float = 1.0):
+    """Best of a few thread counts (a 128-core host is not fastest with 128 threads on the bounded sample)."""
+    cores = os.cpu_count() or 1
+    cands = sorted({cores, max(1, cores // 2), max(1, cores // 4)} if cores > 16 else {cores}, reverse=True)
+    best = None
+    spent = 0.0
+    for th in cands:
+        v, s, desc = _cpu_sample_once(workload, th)
+        spent += s
+        if best is None or v > best[0]:
+            best = (v, desc, th)
+    return best[0], spent, best[1]
+
+
+def _cpu_sample_once(workload: str, threads: int):
     """Times a bounded sample of the workload with the oracle (the reference has no CPU path and cannot be imported
     here -- BASELINE.md section 4): a few tower / decoder layers at TRUE 9B dims on a few frames / tokens, scaled
     linearly by layer, frame, chunk and token counts.  Returns (tokens_per_s, seconds_spent, description)."""
@@ -106,7 +122,7 @@ def cpu_sample(workload: str, budget_scale: float = 1.0):
     from oracle import vidi15_ref as R                      # the one place bench.py executes oracle/ (cpu legs)
     from vidi_b200 import synth
     from vidi_b200.config import vidi15_9b, LLMCfg, VisionCfg, AudioCfg
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads)
     full = vidi15_9b()
     F, Cn, T, _ = WORKLOADS[workload]
     nf, vl, al, ll, ntok, nch = 12, 2, 1, 1, 6144, 6          # frames, vit layers, whisper layers, llm layers, tokens, chunk fraction
@@ -136,7 +152,7 @@ def cpu_sample(workload: str, budget_scale: float = 1.0):
     est = (F * full.vis.run_layers * t_vit + Cn * full.aud.layers * t_aud + (n_img + n_aud) * (full.llm.layers - 1) * t_llm
            + full.llm.layers * t_txt * max(1.0, (n_img + n_aud) / ntok))
     tokens = n_img + n_aud + T
-    desc = (f"fp32 oracle, {os.cpu_count()} threads: {vl} SigLIP layers x {nf} frames, 1 Whisper layer x {nch} chunks, 1 Dattn stream layer x "
+    desc = (f"fp32 oracle, {threads} of {os.cpu_count()} host threads (best of a few counts): {vl} SigLIP layers x {nf} frames, 1 Whisper layer x {nch} chunks, 1 Dattn stream layer x "
             f"{ntok} tokens, 1 text layer; scaled linearly to {F} frames x {full.vis.run_layers} layers, {Cn} chunks x "
             f"{full.aud.layers} layers, {n_img + n_aud} tokens x {full.llm.layers - 1} layers (extrapolated)")
     return tokens / est, time.time() - t_all, desc
@@ -161,7 +177,7 @@ def run_reference(args):
     line = dict(metric=METRIC, value=val, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=tokens / val * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=label, frames=F, audio_chunks=Cn, text_tokens=T, total_tokens=tokens),
-                cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count(), kind="port", sample=desc),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=int(desc.split(" of ")[0].split()[-1]), kind="port", sample=desc),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
                 note="the reference has no CPU path and cannot be imported under this image's transformers (SURVEY.md 8c); "
                      "this arm times the oracle port of its forward on the host cores, extrapolated from a bounded sample")
@@ -189,6 +205,10 @@ def run_ours(args):
     if args.gemm != "auto":
         ops.USE_2CTA = args.gemm == "2cta"
     cfg = vidi15_9b()
+    clips = 1
+    if args.workload == "c4":
+        from vidi_b200.config import Vidi7BConfig
+        cfg, clips = Vidi7BConfig(), 8
     F, Cn, T, label = WORKLOADS[args.workload]
     t0 = time.time()
     sd = synth.make_state_dict(cfg, seed=1234, device=dev, dtype=torch.bfloat16)
@@ -216,14 +236,18 @@ def run_ours(args):
     dev_img = host_img[0].to(dev)
     dev_mel = host_mel[0].to(dev)
     ids_dev = ids[0][ids[0] != -200].to(dev)
-    n_tokens = plan.n_img_total + plan.n_aud_total + T
+    n_tokens = (plan.n_img_total + plan.n_aud_total + T) * clips
 
     def step_device():
-        return eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, logits_to_keep=0)
+        for _ in range(clips):
+            out = eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, logits_to_keep=0)
+        return out
 
     def step_e2e():
-        out = model.forward(ids, images=host_img, audios=host_mel, audio_sizes=[asz], mm_total=(F, Cn))
-        return out.logits[0, -1].float().cpu()                       # device->host read of the step's result
+        for _ in range(clips):
+            out = model.forward(ids, images=host_img, audios=host_mel, audio_sizes=[asz], mm_total=(F, Cn))
+            res = out.logits[0, -1].float().cpu()                    # device->host read of the step's result
+        return res
 
     def barrier():
         if world > 1:
@@ -286,20 +310,21 @@ def run_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e, _, _ = timed(step_e2e, args.steps)
-    h2d = dev_img.numel() * 2 + dev_mel.numel() * 2 + ids.numel() * 8
-    d2h = cfg.llm.vocab * 4
+    h2d = (dev_img.numel() * 2 + dev_mel.numel() * 2 + ids.numel() * 8) * clips
+    d2h = cfg.llm.vocab * 4 * clips
     if rank != 0:
         return
     value = n_tokens * args.steps / (ms / 1e3)
     e2e_v = n_tokens * args.steps / (ms_e2e / 1e3)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and not args.quick:
+    if world == 1 and not args.no_cpu_baseline and not args.quick and clips == 1:
         v, spent, desc = cpu_sample(args.workload)
-        cpu = dict(value=round(v, 3), unit=UNIT, cores=os.cpu_count(), kind="port", sample=desc, seconds=round(spent, 1))
+        cpu = dict(value=round(v, 3), unit=UNIT, cores=int(desc.split(" of ")[0].split()[-1]), kind="port", sample=desc, seconds=round(spent, 1))
     line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=round(ms / args.steps, 2), higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload=label, model="Vidi1.5-9B (Gemma2-9B Dattn + SigLIP-so400m/14@384 + Whisper-large-v3 enc), random init",
+                config=dict(workload=label, model=("Vidi1.5-9B (Gemma2-9B Dattn + SigLIP-so400m/14@384 + Whisper-large-v3 enc), random init" if clips == 1 else
+                                   "Vidi-7B (Mistral-7B Dattn + SigLIP-so400m/14@384 + Whisper-large-v3 enc), random init"),
                             frames=F, audio_chunks=Cn, text_tokens=T, image_tokens=plan.n_img_total, audio_tokens=plan.n_aud_total,
                             total_tokens=n_tokens, parallelism=f"stream-shard x{world} (frames/chunks/tokens), text replicated",
                             l2="inputs and activations >> 126 MB L2; no explicit flush"),

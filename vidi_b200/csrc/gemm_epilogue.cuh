@@ -68,10 +68,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         }
     } else {
         const int col0 = n_blk * BLOCK_N;
+        // The residual row segment of chunk c+1 is requested before chunk c is processed, so its HBM latency overlaps the
+        // TMEM load + math + stores of the current chunk instead of serialising four ~1 us round trips per tile.
+        const __nv_bfloat16* res_row =
+            (p.residual && row_ok) ? p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr : nullptr;
+        uint4 rq_next[4];
+        const int c_begin = wg * (BLOCK_N / 2), c_end = (wg + 1) * (BLOCK_N / 2);
+        if (res_row && col0 + c_begin + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rq_next[j] = *reinterpret_cast<const uint4*>(res_row + col0 + c_begin + j * 8);
+        }
 #pragma unroll 1
-        for (int c = wg * (BLOCK_N / 2); c < (wg + 1) * (BLOCK_N / 2); c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(taddr + c, r);
+            uint4 rq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rq[j] = rq_next[j];
+            if (res_row && c + 32 < c_end && col0 + c + 64 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rq_next[j] = *reinterpret_cast<const uint4*>(res_row + col0 + c + 32 + j * 8);
+            }
             tmem_ld_wait();
             const int cbase = col0 + c;
             if (row_ok && cbase < p.N) {
@@ -110,7 +127,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                     if (full) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
-                            const uint4 q = *reinterpret_cast<const uint4*>(rp + j);
+                            const uint4 q = rq[j >> 3];
                             float2 f;
                             f = unpack_bf16(q.x); v[j] += f.x; v[j + 1] += f.y;
                             f = unpack_bf16(q.y); v[j + 2] += f.x; v[j + 3] += f.y;
