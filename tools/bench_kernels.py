@@ -121,6 +121,7 @@ def one(name):
         "kv_proj": lambda: gemm_launcher(15750, 4096, 3584, 0),
         "vit_fc2": lambda: gemm_launcher(46656, 1152, 4304, 0),
         "vit_qkv": lambda: gemm_launcher(46656, 3456, 1152, 0),
+        "gate_up126k": lambda: gemm_launcher(126000, 28672, 3584, 1, cta2=False),
     }
     if name in cases:
         fn = cases[name]()
@@ -131,6 +132,10 @@ def one(name):
         q = torch.randn(32, 4096, device="cuda").to(BF); kv = torch.randn(126000, 4096, device="cuda").to(BF)
         op = torch.empty(37, 32, 16, 256, device="cuda"); ls = torch.empty(37, 32, 16, device="cuda")
         fn = lambda: ops.xattn_splitkv(q, kv[:, :2048], kv[:, 2048:], None, 16, 8, 256, 1 / 16, 50.0, 37, opart=op, lse=ls)
+    elif name == "layernorm":
+        x = torch.randn(128 * 729, 1152, device="cuda").to(BF); w = torch.ones(1152, device="cuda"); b = torch.zeros(1152, device="cuda")
+        y = torch.empty_like(x)
+        fn = lambda: ops.layernorm(x, w, b, 1e-6, out=y)
     elif name == "residual_norm":
         x = torch.randn(126000, 3584, device="cuda").to(BF); y = torch.randn(126000, 3584, device="cuda").to(BF)
         w = torch.randn(3584, device="cuda").to(BF); h = torch.empty_like(x)
@@ -142,10 +147,10 @@ def one(name):
     torch.cuda.synchronize()
 
 
-def gemm_launcher(M, N, K, glu):
+def gemm_launcher(M, N, K, glu, cta2=None):
     a = torch.randn(M, K, device="cuda").to(BF); w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
     out = torch.empty(M, N // 2 if glu else N, device="cuda", dtype=BF)
-    return lambda: ops.gemm(a, w, out=out, glu=glu)
+    return lambda: ops.gemm(a, w, out=out, glu=glu, cta2=cta2)
 
 
 if len(sys.argv) > 2 and sys.argv[1] == "one":

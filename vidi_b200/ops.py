@@ -77,8 +77,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         e0.record()
     if cta2 is None:
         cta2 = USE_2CTA and M >= 1024 and block_n in (128, 192, 256)
-        if cta2 and block_n == 192:
-            block_n = 256               # measured: the pair kernel prefers 256-wide tiles even with a ragged last tile
     fn = L.vidi_gemm_bf16_2cta if cta2 else L.vidi_gemm_bf16
     rc = fn(_ptr(a), _rowmajor(a), _ptr(w), _rowmajor(w), _ptr(out), _rowmajor(out), M, N, K,
                           _ptr(bias), _ptr(residual), _rowmajor(residual) if residual is not None else 0, res_mod,
