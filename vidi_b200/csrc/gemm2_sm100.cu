@@ -185,7 +185,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             int m_blk, n_blk;
             tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
-            mbar_wait(&tmem_full[acc], acc_phase);
+            mbar_wait_warp(&tmem_full[acc], acc_phase);          // one polling lane per warp
             tc_fence_after();
             const int row = m_blk * 2 * BLOCK_M + row_in_tile;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
@@ -238,7 +238,12 @@ int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
     g2::GemmParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.res_mod = res_mod;
-    p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu; p.group_m = 8;
+    p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu;
+    {   // pair-blocks (256 rows) per L2-resident group, same 48 MB budget as the 1-CTA kernel
+        const int64_t per_block = (int64_t)2 * g2::BLOCK_M * K * 2;
+        int64_t gm = (48ll << 20) / per_block;
+        p.group_m = (int)(gm < 4 ? 4 : gm > 32 ? 32 : gm);
+    }
     if (block_n == 256) return g2::launch<256>(A, lda, W, ldw, p, st);
     if (block_n == 192) return g2::launch<192>(A, lda, W, ldw, p, st);
     if (block_n == 128) return g2::launch<128>(A, lda, W, ldw, p, st);

@@ -175,7 +175,7 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
         const int nrows = min(p.rows_per_block, (p.T - t0) * p.G);
         const bool active = row < nrows;                   // warp-uniform except in the boundary warp
         const bool warp_active = ew * 32 < nrows;
-        float l = 0.f;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};               // independent partial row sums
         __shared__ float xsum[2][128];
         for (int j = 0; j < ntiles; ++j) {
             const int st = j & 1;
@@ -217,7 +217,7 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
                         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(s - p.m_ref));
                         const bool ok = (kb + i < k_end) && ((mbits >> i) & 1u);
                         pv[e] = ok ? pe : 0.f;
-                        l += pv[e];
+                        l4[e & 3] += pv[e];
                     }
                     const uint4 q = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
                                                pack_bf16(pv[6], pv[7]));
@@ -228,6 +228,7 @@ xattn_splitkv_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __gri
             mbar_arrive(&p_full[st]);
         }
         // ---- epilogue: normalise O (TMEM) by the row sum and write the partial ----
+        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         xsum[ch][row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float lt = xsum[0][row] + xsum[1][row];

@@ -259,7 +259,10 @@ def config_from_hf_json(cfg_json: dict) -> Vidi15Config:
                  query_pre_attn_scalar=g("query_pre_attn_scalar", 256), attn_softcap=g("attn_logit_softcapping", 50.0),
                  final_softcap=g("final_logit_softcapping", 30.0), sliding_window=g("sliding_window", 4096),
                  tie_word_embeddings=g("tie_word_embeddings", True))
-    return Vidi15Config(llm=llm, vis=VisionCfg(), aud=AudioCfg(), mm_image_pool_size=g("mm_image_pool_size", 2),
+    # tower dims: the public SigLIP-so400m/14@384 and Whisper-large-v3 configs unless the checkpoint carries overrides
+    vis = VisionCfg(**g("vision_config")) if isinstance(g("vision_config"), dict) else VisionCfg()
+    aud = AudioCfg(**g("audio_config")) if isinstance(g("audio_config"), dict) else AudioCfg()
+    return Vidi15Config(llm=llm, vis=vis, aud=aud, mm_image_pool_size=g("mm_image_pool_size", 2),
                         mm_audio_pool_size=g("mm_audio_pool_size", 5), mm_time_interval=g("mm_time_interval", 10000),
                         mm_std=g("mm_std", 0.028976401314139366), mm_splits=g("mm_splits", 1))
 

@@ -41,6 +41,8 @@ def _rowmajor(t: torch.Tensor) -> int:
 def pick_block_n(M: int, N: int, glu: bool = False) -> int:
     if glu:
         return 256
+    if M <= 256 and N <= 16384:
+        return 64                       # text stream (M ~ 32): weight-bandwidth bound, spread the N tiles over more SMs
     if N % 256 != 0 and N % 192 == 0 and N < 2048:
         return 192                      # 1152, 3456: exact tiling instead of a half-empty last 256 tile
     if N >= 1024 or N % 256 == 0:
