@@ -223,6 +223,8 @@ def run_ours(args):
     model = DattnGemma2ForCausalLM(cfg, sd, device=dev, rank=rank, world=world, group=group, pop_state_dict=True)
     del sd
     eng = model.engine
+    if args.no_overlap:
+        eng.overlap_text = False
     torch.cuda.synchronize()
     t_load = time.time() - t0
 
@@ -321,8 +323,9 @@ def run_ours(args):
         top_launch = dict(kernel="gemm_bf16_kernel<256> GeGLU epilogue", shape=[M_loc, 2 * cfg.llm.inter, cfg.llm.hidden], bound="tensor",
                           achieved=round(fl / avg_ms / 1e9, 1), peak=pk["tensor"], unit="TFLOP/s", frac=round(fl / avg_ms / 1e9 / pk["tensor"], 4),
                           ms_per_launch=round(avg_ms, 3), launches_per_step=gu[2] // args.steps,
-                          # ncu --set full, profiles/r01_ncu_full_summary_v2.txt (M=126000): dram read 13.65 GB + write 3.61 GB per launch
-                          traffic=17255839000 if (world == 1 and args.workload == "c3") else None,
+                          # ncu dram__bytes (M=126000): 13.65+3.61 GB before the L2-sized tile groups (r01_ncu_full_summary_v2.txt), 7.74+3.60 GB after
+                          # (profiles/r01_ncu_gateup126k_traffic_after_l2_groups.txt)
+                          traffic=11340000000 if (world == 1 and args.workload == "c3") else None,
                           algorithmic_bytes=int(M_loc * cfg.llm.hidden * 2 + 2 * cfg.llm.inter * cfg.llm.hidden * 2 + M_loc * cfg.llm.inter * 2))
     # end-to-end through the public API with host buffers
     if args.quick:
@@ -367,6 +370,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm", default="auto", choices=["auto", "1cta", "2cta"], help="A/B switch for the CTA-pair GEMM")
+    ap.add_argument("--no-overlap", action="store_true", help="A/B: run the text pass after the stream pass instead of on the side stream")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, no e2e / cpu legs (for ncu launch lists; not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -219,7 +219,7 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                 const int kbase = j * C::BN;
                 const bool ragged = kbase + C::BN > p.S;
                 // pass 1: row max over the 128 raw scores
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains (FMNMX latency)
+                float mx = -INFINITY;
 #pragma unroll
                 for (int c = 0; c < 128; c += 32) {
                     uint32_t r[32];
@@ -230,9 +230,8 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                         for (int i = 0; i < 32; ++i) if (kbase + c + i >= p.S) r[i] = 0xff800000u;
                     }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
                 }
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 const float m_new = fmaxf(m, mx);
                 float corr;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"((m - m_new) * p.scale_log2));
@@ -240,7 +239,7 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                 const float neg_m = -m_new * p.scale_log2;
                 mbar_wait(&p_empty[blk], (g & 1) ^ 1);
                 // pass 2: p = 2^(s*scale - m*scale), bf16 -> swizzled smem, row sum
-                float rs4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial row sums (FADD latency)
+                float rs = 0.f;
 #pragma unroll
                 for (int c = 0; c < 128; c += 32) {
                     uint32_t r[32];
@@ -257,7 +256,7 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(r[c8 * 8 + e]), p.scale_log2, neg_m)));
-                            rs4[e & 3] += pv[e];
+                            rs += pv[e];
                         }
                         const int chunk = ((c & 32) >> 3) + c8;                 // 16-byte chunk index within the 64-key atom
                         *reinterpret_cast<uint4*>(spa + ((chunk ^ (row & 7)) << 4)) =
@@ -268,7 +267,7 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                 mbar_arrive(&s_empty[blk]);
                 fence_proxy_async();
                 mbar_arrive(&p_full[blk]);
-                l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+                l = l * corr + rs;
                 if (j > 0) take_o(o, corr_prev, g - 1);
                 corr_prev = corr;
             }

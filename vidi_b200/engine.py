@@ -97,6 +97,7 @@ class Vidi15Engine:
         # GEMM variant per site, from same-box A/B runs of the full step (profiles/): the CTA-pair kernel wins on the tower /
         # projector shapes (K=1152..5120), the 1-CTA kernel sustains more on the long stream-pass GEMMs at M ~ 1e5.
         self.llm_cta2 = False
+        self.overlap_text = True        # text pass on a side stream, one layer behind the stream pass (see prefill)
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
@@ -209,7 +210,12 @@ class Vidi15Engine:
     # ------------------------------------------------------------------------------------------
     # decoder: stream pass
     # ------------------------------------------------------------------------------------------
-    def stream_pass(self, S: torch.Tensor, kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def stream_pass(self, S: torch.Tensor, kv: Optional[torch.Tensor] = None, on_kv=None) -> torch.Tensor:
         """S [n, D] (modified in place) -> K||V cache [L, n, 2*kv_dim] bf16.
         Per layer (gemma.py:183-202 with Q5/Q6 of SURVEY 3.4 dropped): K||V = G(S,w_in) W_kv^T;
         S += G(V W_o'^T, w_post); S += G(MLP(G(S,w_pre)), w_postff).  The last layer only needs K||V."""
@@ -226,6 +232,8 @@ class Vidi15Engine:
         g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
             ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv", cta2=self.llm_cta2)
+            if on_kv is not None:
+                on_kv(l)                 # K||V of layer l is enqueued: the text stream may consume it
             if l == len(Ls) - 1:
                 break
             ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo", cta2=self.llm_cta2)
@@ -253,78 +261,10 @@ class Vidi15Engine:
         """ids [Tq] int64 (sentinel already stripped) -> logits fp32 [Tq or k, vocab].
         seg: list of (row0, n_rows, kmask or None, gate, n_total) describing the image / audio row ranges of the
         local K||V cache.  (gemma.py:160-175, 185-192, 206-221, 236-238, 564-569)"""
-        c = self.cfg.llm
-        Tq = ids.numel()
-        qd, kd, dh = c.q_dim, c.kv_dim, c.head_dim
-        pos0 = 0
-        if text_cache is not None:
-            pos0 = text_cache["len"]
-            assert pos0 + Tq <= text_cache["kv"].shape[1], "text KV cache too small"
-        gm = self.gemma
-        scale = c.query_pre_attn_scalar ** -0.5 if gm else dh ** -0.5
-        cap = (c.attn_softcap or 0.0) if gm else 0.0
-        Ls = self.W.layers
-        H = ops.embed_gather(ids, self.W.embed, self.normalizer)
-        h = ops.rmsnorm(H, Ls[0].n_in, c.rms_eps, gm)
-        rows = Tq * c.heads
-        # one flat fp32 buffer per layer holds every stream's [O | LSE] partials of this rank
-        splits = [ops.xattn_splits(-(-s[4] // self.world), c.kv_heads, self.n_sms) for s in seg]
-        sizes = [sp * rows * (dh + 1) for sp in splits]
-        flat = torch.empty(max(1, sum(sizes)), device=self.device, dtype=torch.float32)
-        gathered = torch.empty(self.world * flat.numel(), device=self.device, dtype=torch.float32) if self.world > 1 else flat
-        att = torch.empty(Tq, qd, device=self.device, dtype=torch.float32)
-        y = torch.empty(Tq, c.hidden, device=self.device, dtype=BF16)
-        for l, L in enumerate(Ls):
-            qkv = ops.gemm(h, L.wqkv, tag="text")
-            if text_cache is not None:
-                tkv = text_cache["kv"][l]
-                tkv[pos0:pos0 + Tq].copy_(qkv[:, qd:])
-                kview, vview, Tk = tkv[:pos0 + Tq, :kd], tkv[:pos0 + Tq, kd:], pos0 + Tq
-                ops.rope_inplace(tkv[pos0:pos0 + Tq], 0, c.kv_heads, dh, self.W.inv_freq, pos0)
-            else:
-                krope = qkv[:, qd:].clone()
-                ops.rope_inplace(krope, 0, c.kv_heads, dh, self.W.inv_freq, pos0)
-                kview, vview, Tk = krope[:, :kd], krope[:, kd:], Tq
-            qrope = qkv[:, :qd].clone()
-            ops.rope_inplace(qrope, 0, c.heads, dh, self.W.inv_freq, pos0)
-            window = (c.sliding_window if l % 2 == 0 else 0) if gm else (getattr(c, "sliding_window", 0) or 0)
-            ops.attn_text(qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, scale, cap, window, out=att)
-            off = 0
-            for (r0, nr, kmask, gate, _), sp, sz in zip(seg, splits, sizes):
-                op = flat[off:off + sp * rows * dh]
-                ls = flat[off + sp * rows * dh:off + sz]
-                kvl = kv[l]
-                ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
-                                  scale, cap, sp, opart=op, lse=ls)
-                off += sz
-            if self.world > 1:
-                torch.distributed.all_gather_into_tensor(gathered, flat, group=self.group)
-            off = 0
-            for (r0, nr, kmask, gate, _), sp, sz in zip(seg, splits, sizes):
-                ops.xattn_merge(gathered[off:], gathered[off + sp * rows * dh:], att, gate=gate, accumulate=True,
-                                P=self.world * sp, splits_per_rank=sp, rank_stride_o=flat.numel(),
-                                rank_stride_l=flat.numel(), rows=rows, dh=dh)
-                off += sz
-            a = ops.cast_bf16(att)
-            ops.gemm(a, L.wo, out=y, tag="text")
-            h2 = torch.empty_like(H)
-            w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else self.W.final_norm
-            if gm:
-                ops.residual_norm(H, y, L.n_post, L.n_preff, h2, c.rms_eps, 1, True)
-            else:       # H = residual + (a_t + a_i + a_a) W_o^T ; h2 = post_attention_layernorm(H)   (mistral.py:263,131-133)
-                ops.residual_norm(H, y, None, L.n_post, h2, c.rms_eps, 0, False)
-            g = ops.gemm(h2, L.wgu, glu=self.glu, tag="text")
-            ops.gemm(g, L.wd, out=y, tag="text")
-            if gm:
-                ops.residual_norm(H, y, L.n_postff, w_next, h, c.rms_eps, 1, True)
-            else:
-                ops.residual_norm(H, y, None, w_next, h, c.rms_eps, 0, False)
-        if text_cache is not None:
-            text_cache["len"] = pos0 + Tq
-        hn = h if not logits_to_keep else h[-logits_to_keep:]
-        if gm:          # 30 * tanh(logits / 30)   (gemma.py:566-569)
-            return ops.gemm(hn, self.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True, tag="text")
-        return ops.gemm(hn, self.W.lm_head, out_fp32=True, tag="text")      # logits.float() (mistral.py:615-616)
+        run = _TextRun(self, ids, kv, seg, text_cache, logits_to_keep)
+        for l in range(len(self.W.layers)):
+            run.layer(l)
+        return run.finish()
 
     # ------------------------------------------------------------------------------------------
     # whole prefill for one sample
@@ -358,8 +298,125 @@ class Vidi15Engine:
         Cn = n_chunks_total if n_chunks_total is not None else (mels.shape[0] if mels is not None else 0)
         plan = make_plan(self.cfg, F, Cn, audio_size or 0, self.rank, self.world)
         S, seg = self.encode_streams(images, mels, plan, image_valid, audio_valid)
-        kv = self.stream_pass(S)
-        logits = self.text_pass(ids, kv, seg, text_cache=text_cache, logits_to_keep=logits_to_keep)
+        if self.overlap_text and S.shape[0] > 0:
+            # The text stream's layer l only needs K||V of layer l: run it on a side stream one step behind the stream
+            # pass, so its ~700 small launches (and, multi-GPU, the per-layer all-gather) hide under the big GEMMs.
+            c = self.cfg.llm
+            kv = torch.empty(c.layers, S.shape[0], 2 * c.kv_dim, device=self.device, dtype=BF16)
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                run = _TextRun(self, ids, kv, seg, text_cache, logits_to_keep)
+
+            def on_kv(l):
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    run.layer(l)
+            self.stream_pass(S, kv=kv, on_kv=on_kv)
+            with torch.cuda.stream(side):
+                logits = run.finish()
+            main.wait_stream(side)
+            logits.record_stream(main)
+        else:
+            kv = self.stream_pass(S)
+            logits = self.text_pass(ids, kv, seg, text_cache=text_cache, logits_to_keep=logits_to_keep)
         if return_state:
             return logits, dict(kv=kv, seg=seg, plan=plan, streams=S)
         return logits
+
+
+class _TextRun:
+    """The text stream of one prefill / decode step, advanced layer by layer (so that it can trail the stream pass on a
+    side stream).  Semantics: gemma.py:160-175 (T2T), :185-192 / :206-221 (T2V / T2A), :236-238 (combine), :564-569 (lm_head);
+    Mistral family: mistral.py:190-264."""
+
+    def __init__(self, eng: Vidi15Engine, ids: torch.Tensor, kv: torch.Tensor, seg: list, text_cache: Optional[dict],
+                 logits_to_keep: int):
+        self.e, self.kv, self.seg, self.text_cache, self.keep = eng, kv, seg, text_cache, logits_to_keep
+        c = eng.cfg.llm
+        self.c = c
+        self.Tq = ids.numel()
+        self.pos0 = 0
+        if text_cache is not None:
+            self.pos0 = text_cache["len"]
+            assert self.pos0 + self.Tq <= text_cache["kv"].shape[1], "text KV cache too small"
+        gm = eng.gemma
+        self.scale = c.query_pre_attn_scalar ** -0.5 if gm else c.head_dim ** -0.5
+        self.cap = (c.attn_softcap or 0.0) if gm else 0.0
+        Ls = eng.W.layers
+        self.H = ops.embed_gather(ids, eng.W.embed, eng.normalizer)
+        self.h = ops.rmsnorm(self.H, Ls[0].n_in, c.rms_eps, gm)
+        self.rows = self.Tq * c.heads
+        dh = c.head_dim
+        # one flat fp32 buffer per layer holds every stream's [O | LSE] partials of this rank
+        self.splits = [ops.xattn_splits(-(-s[4] // eng.world), c.kv_heads, eng.n_sms) for s in seg]
+        self.sizes = [sp * self.rows * (dh + 1) for sp in self.splits]
+        self.flat = torch.empty(max(1, sum(self.sizes)), device=eng.device, dtype=torch.float32)
+        self.gathered = (torch.empty(eng.world * self.flat.numel(), device=eng.device, dtype=torch.float32)
+                         if eng.world > 1 else self.flat)
+        self.att = torch.empty(self.Tq, c.q_dim, device=eng.device, dtype=torch.float32)
+        self.y = torch.empty(self.Tq, c.hidden, device=eng.device, dtype=BF16)
+        self.h2 = torch.empty_like(self.H)
+
+    def layer(self, l: int):
+        e, c = self.e, self.c
+        gm = e.gemma
+        Ls = e.W.layers
+        L = Ls[l]
+        Tq, pos0, rows = self.Tq, self.pos0, self.rows
+        qd, kd, dh = c.q_dim, c.kv_dim, c.head_dim
+        qkv = ops.gemm(self.h, L.wqkv, tag="text")
+        if self.text_cache is not None:
+            tkv = self.text_cache["kv"][l]
+            tkv[pos0:pos0 + Tq].copy_(qkv[:, qd:])
+            kview, vview = tkv[:pos0 + Tq, :kd], tkv[:pos0 + Tq, kd:]
+            ops.rope_inplace(tkv[pos0:pos0 + Tq], 0, c.kv_heads, dh, e.W.inv_freq, pos0)
+        else:
+            krope = qkv[:, qd:].clone()
+            ops.rope_inplace(krope, 0, c.kv_heads, dh, e.W.inv_freq, pos0)
+            kview, vview = krope[:, :kd], krope[:, kd:]
+        qrope = qkv[:, :qd].clone()
+        ops.rope_inplace(qrope, 0, c.heads, dh, e.W.inv_freq, pos0)
+        window = (c.sliding_window if l % 2 == 0 else 0) if gm else (getattr(c, "sliding_window", 0) or 0)
+        ops.attn_text(qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, self.scale, self.cap, window, out=self.att)
+        off = 0
+        kvl = self.kv[l]
+        for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
+            op = self.flat[off:off + sp * rows * dh]
+            ls = self.flat[off + sp * rows * dh:off + sz]
+            ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
+                              self.scale, self.cap, sp, opart=op, lse=ls)
+            off += sz
+        if e.world > 1:
+            torch.distributed.all_gather_into_tensor(self.gathered, self.flat, group=e.group)
+        off = 0
+        for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
+            ops.xattn_merge(self.gathered[off:], self.gathered[off + sp * rows * dh:], self.att, gate=gate, accumulate=True,
+                            P=e.world * sp, splits_per_rank=sp, rank_stride_o=self.flat.numel(),
+                            rank_stride_l=self.flat.numel(), rows=rows, dh=dh)
+            off += sz
+        a = ops.cast_bf16(self.att)
+        ops.gemm(a, L.wo, out=self.y, tag="text")
+        w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else e.W.final_norm
+        if gm:
+            ops.residual_norm(self.H, self.y, L.n_post, L.n_preff, self.h2, c.rms_eps, 1, True)
+        else:       # H = residual + (a_t + a_i + a_a) W_o^T ; h2 = post_attention_layernorm(H)   (mistral.py:263,131-133)
+            ops.residual_norm(self.H, self.y, None, L.n_post, self.h2, c.rms_eps, 0, False)
+        g = ops.gemm(self.h2, L.wgu, glu=e.glu, tag="text")
+        ops.gemm(g, L.wd, out=self.y, tag="text")
+        if gm:
+            ops.residual_norm(self.H, self.y, L.n_postff, w_next, self.h, c.rms_eps, 1, True)
+        else:
+            ops.residual_norm(self.H, self.y, None, w_next, self.h, c.rms_eps, 0, False)
+
+    def finish(self) -> torch.Tensor:
+        e, c = self.e, self.c
+        if self.text_cache is not None:
+            self.text_cache["len"] = self.pos0 + self.Tq
+        hn = self.h if not self.keep else self.h[-self.keep:]
+        if e.gemma:     # 30 * tanh(logits / 30)   (gemma.py:566-569)
+            return ops.gemm(hn, e.W.lm_head, act=ops.ACT_SOFTCAP, act_param=c.final_softcap, out_fp32=True, tag="text")
+        return ops.gemm(hn, e.W.lm_head, out_fp32=True, tag="text")      # logits.float() (mistral.py:615-616)
