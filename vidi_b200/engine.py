@@ -97,7 +97,10 @@ class Vidi15Engine:
         # GEMM variant per site, from same-box A/B runs of the full step (profiles/): the CTA-pair kernel wins on the tower /
         # projector shapes (K=1152..5120), the 1-CTA kernel sustains more on the long stream-pass GEMMs at M ~ 1e5.
         self.llm_cta2 = False
-        self.overlap_text = True        # text pass on a side stream, one layer behind the stream pass (see prefill)
+        # Optional: text pass on a side stream, one layer behind the stream pass (see prefill).  Measured NEGATIVE on B200
+        # (profiles/r01_ab_text_overlap_{1,2}gpu.txt: +0.5 % / +2 % step time): the ~700 small kernels that slip in between the
+        # persistent GEMMs delay those kernels' CTAs more than the hidden text latency is worth.  Kept off by default.
+        self.overlap_text = False
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
