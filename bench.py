@@ -327,6 +327,20 @@ def run_ours(args):
                           # (profiles/r01_ncu_gateup126k_traffic_after_l2_groups.txt)
                           traffic=11340000000 if (world == 1 and args.workload == "c3") else None,
                           algorithmic_bytes=int(M_loc * cfg.llm.hidden * 2 + 2 * cfg.llm.inter * cfg.llm.hidden * 2 + M_loc * cfg.llm.inter * 2))
+    # replicated text pass alone (the Amdahl term of the multi-GPU run): CUDA events around engine.text_pass on a prebuilt cache
+    text_ms = None
+    if not args.quick:
+        _, st_ = eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, return_state=True)
+        eng.text_pass(ids_dev, st_["kv"], st_["seg"])
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(3):
+            eng.text_pass(ids_dev, st_["kv"], st_["seg"])
+        b_.record()
+        barrier()
+        text_ms = round(a_.elapsed_time(b_) / 3, 2)
+        del st_
     # end-to-end through the public API with host buffers
     if args.quick:
         ms_e2e = ms
@@ -357,7 +371,8 @@ def run_ours(args):
                          d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors"),
                 other_ops_ms_per_step={k: v[0] for k, v in sorted(getattr(timed, "by_op", {}).items(), key=lambda kv: -kv[1][0])},
                 gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
-                gemm_variant="2cta (cta_group::2) for M>=1024, 1cta otherwise" if ops.USE_2CTA else "1cta")
+                text_pass_ms=text_ms,
+                gemm_variant="2cta (cta_group::2) on tower/projector sites with M>=1024, 1cta on stream-pass and text sites" if ops.USE_2CTA else "1cta")
     print(json.dumps(line), flush=True)
 
 

@@ -105,6 +105,15 @@ int vidi_xattn_splitkv_mma(const void* Q, int64_t ldq, const void* K, const void
  * LSE + rank*rank_stride_l + split*rows (strides in floats): the all-gathered per-rank [O | LSE] blocks merge in place. */
 int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per_rank, int64_t rank_stride_o,
                      int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream);
+/* fused text-stream helpers (fewer launches per layer / per decoded token):
+ *  vidi_text_qk_prep: q_rope = RoPE(q); kv_out rows = RoPE(k) | v, read from the fused qkv projection (HF apply_rotary_pos_emb,
+ *                     gemma.py:165-175);
+ *  vidi_xattn_merge2: out_bf16 = bf16(att_text + sum_s gate_s * LSE-merge(partials_s)) for up to two streams (gemma.py:236). */
+int vidi_text_qk_prep(const void* qkv, int64_t ld, void* q_rope, int64_t ldq, void* kv_out, int64_t ldkv, int Tq, int Hq, int Hkv,
+                      int dh, const float* inv_freq, int pos0, void* stream);
+int vidi_xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0, const float* O1,
+                      const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
+                      int rows, int dh, void* out_bf16, void* stream);
 int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream);
 /* causal text self attention with soft-cap and sliding window (HF Gemma2Attention via gemma.py:165-175), K16 */
 int vidi_attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int Tq, int Tk, int pos0, int Hq,

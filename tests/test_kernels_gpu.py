@@ -321,3 +321,31 @@ def test_rope_and_attn_text():
         ref = R.attend(qkv[:, :qd].float().cpu().view(T, Hq, dh).transpose(0, 1),
                        qkv[:, qd:qd + kd].float().cpu().view(T, Hkv, dh).transpose(0, 1), vh, 1 / 16, 50.0, bias)
         assert rel_err(out.cpu(), ref) < 5e-3
+
+
+def test_text_qk_prep_and_merge2_match_unfused_path():
+    """The fused text helpers must equal the individual kernels they replace (clone+rope+copy, merge x2 + cast)."""
+    from vidi_b200 import ops
+    T, Hq, Hkv, dh = 19, 4, 2, 256
+    qd, kd = Hq * dh, Hkv * dh
+    qkv = rnd(T, qd + 2 * kd, seed=60).to(BF)
+    inv = (1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.float) / dh))).cuda()
+    q_ref = qkv[:, :qd].clone(); kv_ref = qkv[:, qd:].clone()
+    ops.rope_inplace(q_ref, 0, Hq, dh, inv, 7); ops.rope_inplace(kv_ref, 0, Hkv, dh, inv, 7)
+    q_out = torch.empty(T, qd, device="cuda", dtype=BF); kv_out = torch.empty(T, 2 * kd, device="cuda", dtype=BF)
+    ops.text_qk_prep(qkv, q_out, kv_out, Hq, Hkv, dh, inv, 7)
+    assert torch.equal(q_out, q_ref) and torch.equal(kv_out, kv_ref)
+    rows = T * Hq
+    att = rnd(rows, dh, seed=61).float().contiguous()
+    srcs, ref = [], att.clone()
+    for i, (P, gate) in enumerate([(5, 1.0), (3, 0.5)]):
+        O = rnd(P, rows, dh, seed=62 + i).float().contiguous(); Ls = rnd(P, rows, seed=64 + i).float().contiguous()
+        Ls[1, ::3] = float("-inf")
+        ops.xattn_merge(O, Ls, ref, gate=gate, accumulate=True)
+        srcs.append((O, Ls, P, P, 0, 0, gate))
+    out = torch.empty(rows, dh, device="cuda", dtype=BF)
+    ops.xattn_merge2(srcs, att, out, rows, dh)
+    assert rel_err(out, ref) < 4e-3
+    out1 = torch.empty(rows, dh, device="cuda", dtype=BF)
+    ops.xattn_merge2([], att, out1, rows, dh)
+    assert torch.equal(out1, att.to(BF))

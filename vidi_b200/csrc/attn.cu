@@ -485,6 +485,96 @@ attn_text_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bf
     }
 }
 
+// fused text q/k preparation (one launch instead of clone + rope + copy + rope): from qkv [Tq, qd + 2*kd]
+//   q_rope [Tq, qd]          = RoPE(q)                      (cross attention keeps using the un-roped q inside qkv)
+//   kv_out [Tq, 2*kd] rows   = RoPE(k) | v                  (written straight into the text K||V cache rows pos0..)
+__global__ void text_qk_prep_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, __nv_bfloat16* __restrict__ q_rope,
+                                    int64_t ldq, __nv_bfloat16* __restrict__ kv_out, int64_t ldkv, int Hq, int Hkv, int DH,
+                                    const float* __restrict__ inv_freq, int pos0) {
+    const int t = blockIdx.x, hh = blockIdx.y;
+    const int half = DH / 2;
+    const int qd = Hq * DH, kd = Hkv * DH;
+    const __nv_bfloat16* src;
+    __nv_bfloat16* dst;
+    bool rope = true;
+    if (hh < Hq) { src = qkv + (int64_t)t * ld + hh * DH; dst = q_rope + (int64_t)t * ldq + hh * DH; }
+    else if (hh < Hq + Hkv) { const int h = hh - Hq; src = qkv + (int64_t)t * ld + qd + h * DH; dst = kv_out + (int64_t)t * ldkv + h * DH; }
+    else { const int h = hh - Hq - Hkv; src = qkv + (int64_t)t * ld + qd + kd + h * DH; dst = kv_out + (int64_t)t * ldkv + kd + h * DH; rope = false; }
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const float a = __bfloat162float(src[i]), b = __bfloat162float(src[i + half]);
+        if (rope) {
+            float sn, cs;
+            sincosf((float)(pos0 + t) * inv_freq[i], &sn, &cs);
+            cs = __bfloat162float(__float2bfloat16(cs)); sn = __bfloat162float(__float2bfloat16(sn));
+            dst[i] = __float2bfloat16(a * cs - b * sn);
+            dst[i + half] = __float2bfloat16(b * cs + a * sn);
+        } else {
+            dst[i] = src[i];
+            dst[i + half] = src[i + half];
+        }
+    }
+}
+
+// fused merge of up to two streams' partials + text attention + bf16 cast (one launch instead of merge x2 + cast):
+//   out_bf16[row, :] = bf16( att_text[row, :] + sum_s gate_s * merge(partials_s)[row, :] )
+struct MergeSrc {
+    const float* O; const float* L; int P; int spr; int64_t rso; int64_t rsl; float gate;
+};
+__global__ void __launch_bounds__(128)
+xattn_merge2_kernel(MergeSrc s0, MergeSrc s1, int nsrc, const float* __restrict__ att, int rows, int DH,
+                    __nv_bfloat16* __restrict__ out) {
+    const int row = blockIdx.x;
+    extern __shared__ float wts2[];               // [P0 + P1]
+    __shared__ float red[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float inv[2] = {0.f, 0.f};
+    int base = 0;
+    for (int si = 0; si < nsrc; ++si) {
+        const MergeSrc& s = si == 0 ? s0 : s1;
+        float* w = wts2 + base;
+        float lmax = -INFINITY;
+        for (int p = tid; p < s.P; p += 128) {
+            const float l = s.L[(p / s.spr) * s.rsl + (int64_t)(p % s.spr) * rows + row];
+            w[p] = l; lmax = fmaxf(lmax, l);
+        }
+        lmax = warp_max(lmax);
+        if (lane == 0) red[warp] = lmax;
+        __syncthreads();
+        const float Lm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        __syncthreads();
+        float dsum = 0.f;
+        for (int p = tid; p < s.P; p += 128) {
+            const float l = w[p];
+            const float e = (l == -INFINITY) ? 0.f : __expf(l - Lm);
+            w[p] = e; dsum += e;
+        }
+        dsum = warp_sum(dsum);
+        if (lane == 0) red[warp] = dsum;
+        __syncthreads();
+        const float den = red[0] + red[1] + red[2] + red[3];
+        inv[si] = den > 0.f ? s.gate / den : 0.f;
+        __syncthreads();
+        base += s.P;
+    }
+    for (int c = tid * 2; c < DH; c += 256) {
+        float2 acc = *reinterpret_cast<const float2*>(att + (int64_t)row * DH + c);
+        base = 0;
+        for (int si = 0; si < nsrc; ++si) {
+            const MergeSrc& s = si == 0 ? s0 : s1;
+            const float* w = wts2 + base;
+            float2 a = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int p = 0; p < s.P; ++p) {
+                const float2 v = *reinterpret_cast<const float2*>(s.O + (p / s.spr) * s.rso + ((int64_t)(p % s.spr) * rows + row) * DH + c);
+                a.x += w[p] * v.x; a.y += w[p] * v.y;
+            }
+            acc.x += a.x * inv[si]; acc.y += a.y * inv[si];
+            base += s.P;
+        }
+        *reinterpret_cast<uint32_t*>(out + (int64_t)row * DH + c) = pack_bf16(acc.x, acc.y);
+    }
+}
+
 // =================================================================================================
 // host launchers
 // =================================================================================================
@@ -585,6 +675,28 @@ int attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t 
                                                     (const __nv_bfloat16*)V, ldkv, Tk, pos0, G, scale, softcap, window, out, Hq);
     else
         VB_REQUIRE(false, "attn_text: unsupported head_dim %d", dh);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+
+int text_qk_prep(const void* qkv, int64_t ld, void* q_rope, int64_t ldq, void* kv_out, int64_t ldkv, int Tq, int Hq, int Hkv,
+                 int dh, const float* inv_freq, int pos0, cudaStream_t st) {
+    if (Tq == 0) return 0;
+    text_qk_prep_kernel<<<dim3(Tq, Hq + 2 * Hkv), 64, 0, st>>>((const __nv_bfloat16*)qkv, ld, (__nv_bfloat16*)q_rope, ldq,
+                                                              (__nv_bfloat16*)kv_out, ldkv, Hq, Hkv, dh, inv_freq, pos0);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0, const float* O1,
+                 const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
+                 int rows, int dh, void* out_bf16, cudaStream_t st) {
+    if (rows == 0) return 0;
+    VB_REQUIRE(nsrc >= 0 && nsrc <= 2 && dh % 2 == 0, "xattn_merge2: nsrc=%d dh=%d", nsrc, dh);
+    MergeSrc s0{O0, L0, nsrc > 0 ? P0 : 0, spr0 > 0 ? spr0 : 1, rso0, rsl0, gate0};
+    MergeSrc s1{O1, L1, nsrc > 1 ? P1 : 0, spr1 > 0 ? spr1 : 1, rso1, rsl1, gate1};
+    xattn_merge2_kernel<<<rows, 128, (s0.P + s1.P + 1) * sizeof(float), st>>>(s0, s1, nsrc, att, rows, dh, (__nv_bfloat16*)out_bf16);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -35,6 +35,9 @@ int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const
                   float, float*, float*, int, cudaStream_t);
 int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int, float, int, float*, cudaStream_t);
 int rope_inplace(void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
+int text_qk_prep(const void*, int64_t, void*, int64_t, void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
+int xattn_merge2(const float*, const float*, int, int, int64_t, int64_t, float, const float*, const float*, int, int, int64_t, int64_t,
+                 float, int, const float*, int, int, void*, cudaStream_t);
 int attn_text(const void*, int64_t, const void*, const void*, int64_t, int, int, int, int, int, int, float, float, int, float*,
               cudaStream_t);
 }  // namespace vb
@@ -145,6 +148,16 @@ int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per
                      int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream) {
     return COUNT(vb::xattn_merge(Opart, LSE, P, splits_per_rank, rank_stride_o, rank_stride_l, rows, dh, gate, accumulate, out,
                                  ST(stream)));
+}
+int vidi_text_qk_prep(const void* qkv, int64_t ld, void* q_rope, int64_t ldq, void* kv_out, int64_t ldkv, int Tq, int Hq, int Hkv,
+                      int dh, const float* inv_freq, int pos0, void* stream) {
+    return COUNT(vb::text_qk_prep(qkv, ld, q_rope, ldq, kv_out, ldkv, Tq, Hq, Hkv, dh, inv_freq, pos0, ST(stream)));
+}
+int vidi_xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0, const float* O1,
+                      const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
+                      int rows, int dh, void* out_bf16, void* stream) {
+    return COUNT(vb::xattn_merge2(O0, L0, P0, spr0, rso0, rsl0, gate0, O1, L1, P1, spr1, rso1, rsl1, gate1, nsrc, att, rows, dh,
+                                  out_bf16, ST(stream)));
 }
 int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream) {
     return COUNT(vb::rope_inplace(x, ld, col_off, T, heads, dh, inv_freq, pos0, ST(stream)));

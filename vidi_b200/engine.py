@@ -363,6 +363,9 @@ class _TextRun:
         self.att = torch.empty(self.Tq, c.q_dim, device=eng.device, dtype=torch.float32)
         self.y = torch.empty(self.Tq, c.hidden, device=eng.device, dtype=BF16)
         self.h2 = torch.empty_like(self.H)
+        self.a = torch.empty(self.Tq, c.q_dim, device=eng.device, dtype=BF16)
+        self.qrope = torch.empty(self.Tq, c.q_dim, device=eng.device, dtype=BF16)
+        self.krope = torch.empty(self.Tq, 2 * c.kv_dim, device=eng.device, dtype=BF16) if text_cache is None else None
 
     def layer(self, l: int):
         e, c = self.e, self.c
@@ -372,19 +375,16 @@ class _TextRun:
         Tq, pos0, rows = self.Tq, self.pos0, self.rows
         qd, kd, dh = c.q_dim, c.kv_dim, c.head_dim
         qkv = ops.gemm(self.h, L.wqkv, tag="text")
+        # one launch: q_rope = RoPE(q); text K||V rows = RoPE(k) | v (straight into the cache when there is one)
         if self.text_cache is not None:
             tkv = self.text_cache["kv"][l]
-            tkv[pos0:pos0 + Tq].copy_(qkv[:, qd:])
+            ops.text_qk_prep(qkv, self.qrope, tkv[pos0:pos0 + Tq], c.heads, c.kv_heads, dh, e.W.inv_freq, pos0)
             kview, vview = tkv[:pos0 + Tq, :kd], tkv[:pos0 + Tq, kd:]
-            ops.rope_inplace(tkv[pos0:pos0 + Tq], 0, c.kv_heads, dh, e.W.inv_freq, pos0)
         else:
-            krope = qkv[:, qd:].clone()
-            ops.rope_inplace(krope, 0, c.kv_heads, dh, e.W.inv_freq, pos0)
-            kview, vview = krope[:, :kd], krope[:, kd:]
-        qrope = qkv[:, :qd].clone()
-        ops.rope_inplace(qrope, 0, c.heads, dh, e.W.inv_freq, pos0)
+            ops.text_qk_prep(qkv, self.qrope, self.krope, c.heads, c.kv_heads, dh, e.W.inv_freq, pos0)
+            kview, vview = self.krope[:, :kd], self.krope[:, kd:]
         window = (c.sliding_window if l % 2 == 0 else 0) if gm else (getattr(c, "sliding_window", 0) or 0)
-        ops.attn_text(qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, self.scale, self.cap, window, out=self.att)
+        ops.attn_text(self.qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, self.scale, self.cap, window, out=self.att)
         off = 0
         kvl = self.kv[l]
         for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
@@ -393,15 +393,15 @@ class _TextRun:
             ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
                               self.scale, self.cap, sp, opart=op, lse=ls)
             off += sz
-        if e.world > 1:
+        if e.world > 1 and self.seg:
             torch.distributed.all_gather_into_tensor(self.gathered, self.flat, group=e.group)
-        off = 0
+        # one launch: a = bf16(att_text + gate_img * merge(img partials) + gate_aud * merge(aud partials))
+        srcs, off = [], 0
         for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
-            ops.xattn_merge(self.gathered[off:], self.gathered[off + sp * rows * dh:], self.att, gate=gate, accumulate=True,
-                            P=e.world * sp, splits_per_rank=sp, rank_stride_o=self.flat.numel(),
-                            rank_stride_l=self.flat.numel(), rows=rows, dh=dh)
+            srcs.append((self.gathered[off:], self.gathered[off + sp * rows * dh:], e.world * sp, sp, self.flat.numel(),
+                         self.flat.numel(), gate))
             off += sz
-        a = ops.cast_bf16(self.att)
+        a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
         ops.gemm(a, L.wo, out=self.y, tag="text")
         w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else e.W.final_norm
         if gm:

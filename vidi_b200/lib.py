@@ -41,6 +41,8 @@ SIGNATURES = {
     "vidi_xattn_splitkv": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_splitkv_mma": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_merge": [_p, _p, _i, _i, _l, _l, _i, _i, _f, _i, _p, _p],
+    "vidi_text_qk_prep": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _p, _i, _p],
+    "vidi_xattn_merge2": [_p, _p, _i, _i, _l, _l, _f, _p, _p, _i, _i, _l, _l, _f, _i, _p, _i, _i, _p, _p],
     "vidi_rope_inplace": [_p, _l, _i, _i, _i, _i, _p, _i, _p],
     "vidi_attn_text": [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p],
 }

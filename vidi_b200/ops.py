@@ -296,6 +296,28 @@ def xattn_merge(opart, lse, out, gate: float = 1.0, accumulate: bool = False, P=
     return out
 
 
+def text_qk_prep(qkv, q_rope, kv_out, Hq: int, Hkv: int, dh: int, inv_freq, pos0: int = 0):
+    """qkv [Tq, (Hq+2Hkv)*dh] -> q_rope [Tq, Hq*dh] = RoPE(q); kv_out [Tq, 2*Hkv*dh] = RoPE(k) | v."""
+    L = _lib.load()
+    Tq = qkv.shape[0]
+    _lib.check(L.vidi_text_qk_prep(_ptr(qkv), _rowmajor(qkv), _ptr(q_rope), _rowmajor(q_rope), _ptr(kv_out), _rowmajor(kv_out),
+                                   Tq, Hq, Hkv, dh, _ptr(inv_freq), pos0, _stream()), "text_qk_prep")
+    return q_rope, kv_out
+
+
+def xattn_merge2(srcs, att, out_bf16, rows: int, dh: int):
+    """srcs: up to two (O, LSE, P, splits_per_rank, rank_stride_o, rank_stride_l, gate); out = bf16(att + sum merged)."""
+    L = _lib.load()
+    assert len(srcs) <= 2 and att.dtype == torch.float32 and out_bf16.dtype == BF16
+    pad = (None, None, 0, 1, 0, 0, 0.0)
+    s0 = srcs[0] if len(srcs) > 0 else pad
+    s1 = srcs[1] if len(srcs) > 1 else pad
+    _lib.check(L.vidi_xattn_merge2(_ptr(s0[0]), _ptr(s0[1]), s0[2], s0[3], s0[4], s0[5], s0[6], _ptr(s1[0]), _ptr(s1[1]), s1[2],
+                                   s1[3], s1[4], s1[5], s1[6], len(srcs), _ptr(att), rows, dh, _ptr(out_bf16), _stream()),
+               "xattn_merge2")
+    return out_bf16
+
+
 def rope_inplace(x, col_off: int, heads: int, dh: int, inv_freq, pos0: int = 0):
     L = _lib.load()
     T = x.shape[0]
@@ -349,5 +371,5 @@ def _instrument(fn):
 
 for _name in ("rmsnorm", "residual_norm", "layernorm", "mm_finish", "rmsnorm_f32", "patch_im2col", "whisper_im2col1",
               "whisper_im2col2", "pool_s2d", "conv_window_gather", "bilinear_ac", "embed_gather", "sinusoid_split", "split3",
-              "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text"):
+              "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text", "text_qk_prep", "xattn_merge2"):
     globals()[_name] = _instrument(globals()[_name])
