@@ -263,6 +263,32 @@ def test_attn_dense(B, S, H, dh, impl):
     assert rel_err(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("S,H,dh,mode", [(729, 4, 72, "rising"), (1500, 4, 64, "rising"), (729, 4, 72, "falling"),
+                                         (700, 2, 64, "spiky")])
+def test_attn_dense_reference_moves(S, H, dh, mode):
+    """Score ranges that drift by far more than 2^8 between key tiles: exercises the lazy re-referencing of the
+    ping-pong softmax (attn2_sm100.cu) both ways (reference must move / must not move)."""
+    from vidi_b200 import ops
+    B, d = 3, H * dh
+    g = torch.Generator(device="cuda").manual_seed(91)
+    qkv = torch.randn(B * S, 3 * d, device="cuda", generator=g)
+    pos = torch.arange(S, device="cuda", dtype=torch.float32).repeat(B)
+    if mode == "rising":
+        gain = 0.2 + pos / 64.0                      # later keys much larger
+    elif mode == "falling":
+        gain = 0.2 + (S - pos) / 64.0
+    else:
+        gain = torch.where((pos.long() % 197) == 190, 30.0, 0.5)   # isolated huge keys in late tiles
+    qkv[:, d:2 * d] *= gain[:, None]
+    qkv[:, :d] = qkv[:, :d].abs()                    # positive q·k drift: |q|·k with k scaled → wide logit range
+    qkv = qkv.to(BF)
+    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5)
+    q, k, v = [t.float().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, d)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, ref) < 1e-2
+
+
 @pytest.mark.parametrize("impl", ["auto", "mma"])
 @pytest.mark.parametrize("T,N,Hq,Hkv,dh,cap,splits", [
     (32, 5000, 16, 8, 256, 50.0, 7), (12, 300, 4, 2, 256, 50.0, 3), (40, 2048, 32, 8, 128, 0.0, 4),

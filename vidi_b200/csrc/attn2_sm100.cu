@@ -3,7 +3,17 @@
 // cross-warpgroup max exchange and no block barrier in the tile loop; the MMA issuer alternates between the two blocks
 //     QK_A(j+1) | softmax_B(j)      PV_A(j) | softmax_A(j+1) ...
 // and every K/V tile brought in by TMA is used by both blocks (half the shared-memory fill traffic per query).
-//   TMEM: S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464); smem: Q 2 items x 2 blocks, K/V 2 stages, P_A, P_B.
+//   TMEM: S_A [0,128) S_B [128,256) O_A [256,352) O_B [384,480); smem: Q 2 items x 2 blocks, K/V 2 stages, P_A, P_B, ones.
+// Softmax inner loop (the bound: MUFU ex2 + issue slots), per score: FFMA, MUFU.EX2, 1/2 CVT.bf16x2, 1/4 LOP3 —
+//   * the row sum l is not added up by the threads but by the tensor core, as extra all-ones columns of V, so l arrives in
+//     TMEM next to O and is rescaled with it.  dh=72: the V tail tile [128 keys][cols 64..79] has 8 zero-filled (TMA OOB)
+//     columns 72..79 which a helper warp overwrites with 1.0 after each V tile lands; dh=64: one more N=16 MMA per k-step
+//     against a constant all-ones operand;
+//   * the reference m is exact for the first key tile and afterwards only moved when some p would exceed 2^8 ("lazy
+//     re-referencing"); p is computed pre-scaled by 2^-7 so that test is one bit of the packed bf16 words (exponent MSB),
+//     OR-ed together as they are stored; the exact-max pass + redo only runs on a tile where that bit fired;
+//   * TMEM loads are software-pipelined (next 32 columns in flight while the current ones are exponentiated), and
+//     setmaxnreg moves registers from the TMA/MMA warps to the softmax warpgroups (no spills).
 #include "common.cuh"
 
 namespace vb {
@@ -22,8 +32,10 @@ struct Fa2Cfg {
     static constexpr int kPBytes = 2 * kMainBytes;             // [128][128] bf16
     // Q: [item parity 2][block 2] slots | K [2] | V [2] | P [2 blocks]
     static constexpr int kOffQ = 0, kOffK = 4 * kSlot, kOffV = 6 * kSlot, kOffP = 8 * kSlot;
-    static constexpr int kOffBar = kOffP + 2 * kPBytes;
-    static constexpr int kSmem = kOffBar + 256 + 1024;        // 160K + 64K + ... = 225.25 KB
+    static constexpr int kOffOnes = kOffP + 2 * kPBytes;       // 512 B of bf16 1.0: B operand of the row-sum MMA
+    static constexpr int kOffBar = kOffOnes + 512;
+    static constexpr int kSmem = kOffBar + 256 + 1024;        // 160K + 64K + ... = 225.75 KB
+    static constexpr int LCOL = DH;                            // TMEM column (within an O block) holding the row sum
 };
 
 struct Fa2Params {
@@ -54,7 +66,8 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
     uint64_t* p_empty = bars + 14;    // [2]
     uint64_t* o_full = bars + 16;     // [2]
     uint64_t* o_empty = bars + 18;    // [2] (128 arrivals)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* v_ones = bars + 20;     // [2] V tail ones written (dh=72)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = threadIdx.x >> 5;
     if (warp == 0 && elect_one()) {
@@ -68,16 +81,23 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
             mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128);
             mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
             mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 128);
+            mbar_init(&v_ones[i], 1);
         }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_ptr);
+    if (warp == 3) {                                                   // 256 x bf16 1.0
+        reinterpret_cast<uint4*>(smem + C::kOffOnes)[lane_id()] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int nkt = p.nkt;
 
+    if (warp < 4) {
+        setmaxnreg_dec<104>();
     if (warp == 0) {
         // ============================ TMA producer ============================
         if (elect_one()) {
@@ -136,12 +156,14 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
             };
             auto issue_pv = [&](int blk, uint32_t gg) {
                 const int st = gg & 1;
+                if (C::TAIL && blk == 0) mbar_wait(&v_ones[st], (gg >> 1) & 1);
                 mbar_wait(&p_full[blk], gg & 1);
                 mbar_wait(&o_empty[blk], (gg & 1) ^ 1);
                 tc_fence_after();
                 const uint8_t* sp = smem + C::kOffP + blk * C::kPBytes;
                 const uint8_t* sv = smem + C::kOffV + st * C::kSlot;
                 const uint32_t d = tmem_base + 256 + blk * 128;
+                const uint64_t b1 = umma_desc_mn_sw32(smem_u32(smem + C::kOffOnes), 2048, 256);   // every element is 1.0
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint64_t a = umma_desc_k_sw128(smem_u32(sp + (kk >> 2) * C::kMainBytes)) + 2 * (kk & 3);
@@ -151,6 +173,7 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                         const uint64_t bt = umma_desc_mn_sw32(smem_u32(sv + C::kMainBytes + kk * 16 * 32), 2048, 256);
                         umma_f16(d + 64, a, bt, idesc_pv_tail, kk != 0);
                     }
+                    if (!C::TAIL) umma_f16(d + C::LCOL, a, b1, idesc_pv_tail, kk != 0);  // row sums of P
                 }
                 umma_commit(&o_full[blk]);
                 umma_commit(&p_empty[blk]);
@@ -174,8 +197,27 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
                 g += nkt;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp == 3 && C::TAIL) {
+        // ============================ V tail: columns 72..79 := 1.0 (row-sum columns) ============================
+        uint32_t g = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            for (int j = 0; j < nkt; ++j, ++g) {
+                const int st = g & 1;
+                mbar_wait(&kv_full[st], (g >> 1) & 1);
+                uint8_t* svt = smem + C::kOffV + st * C::kSlot + C::kMainBytes;
+#pragma unroll
+                for (int r = lane_id(); r < 128; r += 32)                          // SW32: 16-byte chunk index ^= bit 2 of the row
+                    *reinterpret_cast<uint4*>(svt + r * 32 + ((1 ^ ((r >> 2) & 1)) << 4)) =
+                        make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane_id() == 0) mbar_arrive(&v_ones[st]);
+            }
+        }
+    }
+    } else {
         // ============================ softmax / output: warpgroup `blk` owns query block `blk` ============================
+        setmaxnreg_inc<200>();
         const int ew = (warp - 4) & 3;
         const int blk = (warp - 4) >> 2;
         const int row = ew * 32 + lane_id();
@@ -184,24 +226,32 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
         const uint32_t o_addr = tmem_base + 256 + blk * 128 + lane_addr;
         uint8_t* sp_row = smem + C::kOffP + blk * C::kPBytes + row * 128;
         uint32_t g = 0;
-        auto take_o = [&](float (&o)[C::OCOLS], float corr_prev, uint32_t gg) {
+        auto take_o = [&](float (&o)[C::OCOLS], float& l, float corr_prev, uint32_t gg) {
             mbar_wait(&o_full[blk], gg & 1);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t t0[32];
-                tmem_ld_32x32b_x32(o_addr + c, t0);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr_prev + __uint_as_float(t0[i]);
-            }
+            uint32_t t0[32], t1[32];
+            tmem_ld_32x32b_x32(o_addr, t0);
+            tmem_ld_32x32b_x32(o_addr + 32, t1);
+            uint32_t tl = 0;
+            if (!C::TAIL) tl = tmem_ld_32x32b_x1(o_addr + C::LCOL);
+            tmem_ld_wait();
             if (C::TAIL) {
-                uint32_t t1[16];
-                tmem_ld_32x32b_x16(o_addr + 64, t1);
+                uint32_t t2[16];
+                tmem_ld_32x32b_x16(o_addr + 64, t2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = o[i] * corr_prev + __uint_as_float(t0[i]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * corr_prev + __uint_as_float(t1[i]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[64 + i] = o[64 + i] * corr_prev + __uint_as_float(t1[i]);
+                for (int i = 0; i < 16; ++i) o[64 + i] = o[64 + i] * corr_prev + __uint_as_float(t2[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = o[i] * corr_prev + __uint_as_float(t0[i]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[32 + i] = o[32 + i] * corr_prev + __uint_as_float(t1[i]);
             }
+            if (!C::TAIL) l = l * corr_prev + __uint_as_float(tl);
             tc_fence_before();
             mbar_arrive(&o_empty[blk]);
         };
@@ -209,70 +259,93 @@ attn_fwd2_sm100_kernel(const __grid_constant__ CUtensorMap tm_main, const __grid
             const int pr = item % p.npair;
             const int h = (item / p.npair) % p.H;
             const int b = item / (p.npair * p.H);
-            float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+            // a warp whose 32 query rows all lie beyond S keeps the barrier protocol but does no arithmetic
+            const bool dead = (pr * 2 + blk) * C::BM + ew * 32 >= p.S;
+            float m = 0.f, l = 0.f, corr_prev = 1.f;
             float o[C::OCOLS];
 #pragma unroll
             for (int i = 0; i < C::OCOLS; ++i) o[i] = 0.f;
             for (int j = 0; j < nkt; ++j, ++g) {
                 mbar_wait(&s_full[blk], g & 1);
                 tc_fence_after();
-                const int kbase = j * C::BN;
-                const bool ragged = kbase + C::BN > p.S;
-                // pass 1: row max over the 128 raw scores
-                float mx = -INFINITY;
+                const int nvalid = p.S - j * C::BN;                      // keys of this tile inside the sequence (may exceed 128)
+                // exact row max of the tile (first tile of an item, and the rare re-reference)
+                auto row_max = [&]() {
+                    float mx = -INFINITY;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(s_addr, ra);
 #pragma unroll
-                for (int c = 0; c < 128; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(s_addr + c, r);
-                    tmem_ld_wait();
-                    if (ragged) {
+                    for (int cc = 0; cc < 4; ++cc) {
+                        uint32_t (&r)[32] = (cc & 1) ? rb : ra;
+                        uint32_t (&rn)[32] = (cc & 1) ? ra : rb;
+                        tmem_ld_wait();
+                        if (cc < 3) tmem_ld_32x32b_x32(s_addr + (cc + 1) * 32, rn);
+                        if (nvalid >= (cc + 1) * 32) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) if (kbase + c + i >= p.S) r[i] = 0xff800000u;
-                    }
+                            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                }
-                const float m_new = fmaxf(m, mx);
-                float corr;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"((m - m_new) * p.scale_log2));
-                m = m_new;
-                const float neg_m = -m_new * p.scale_log2;
-                mbar_wait(&p_empty[blk], (g & 1) ^ 1);
-                // pass 2: p = 2^(s*scale - m*scale), bf16 -> swizzled smem, row sum
-                float rs = 0.f;
-#pragma unroll
-                for (int c = 0; c < 128; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(s_addr + c, r);
-                    tmem_ld_wait();
-                    if (ragged) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) if (kbase + c + i >= p.S) r[i] = 0xff800000u;
-                    }
-                    uint8_t* spa = sp_row + (c >> 6) * C::kMainBytes;
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        float pv[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e]) : "f"(fmaf(__uint_as_float(r[c8 * 8 + e]), p.scale_log2, neg_m)));
-                            rs += pv[e];
+                            for (int i = 0; i < 32; ++i) if (cc * 32 + i < nvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
                         }
-                        const int chunk = ((c & 32) >> 3) + c8;                 // 16-byte chunk index within the 64-key atom
-                        *reinterpret_cast<uint4*>(spa + ((chunk ^ (row & 7)) << 4)) =
-                            make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
                     }
+                    return mx;
+                };
+                // P = exp2(S*scale - ref - 7) -> bf16 -> swizzled smem; returns the OR of all packed words
+                auto exp_pass = [&](float neg_ref) {
+                    uint32_t ored = 0;
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(s_addr, ra);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        uint32_t (&r)[32] = (cc & 1) ? rb : ra;
+                        uint32_t (&rn)[32] = (cc & 1) ? ra : rb;
+                        tmem_ld_wait();
+                        if (cc < 3) tmem_ld_32x32b_x32(s_addr + (cc + 1) * 32, rn);
+                        uint8_t* spa = sp_row + (cc >> 1) * C::kMainBytes;
+                        if (nvalid < (cc + 1) * 32) {                   // ragged tail of the sequence: mask (warp-uniform branch)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (cc * 32 + i >= nvalid) r[i] = 0xff800000u;
+                        }
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            float pv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pv[e])
+                                    : "f"(fmaf(__uint_as_float(r[c8 * 8 + e]), p.scale_log2, neg_ref)));
+                            const uint4 w = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                                                       pack_bf16(pv[6], pv[7]));
+                            ored |= (w.x | w.y) | (w.z | w.w);
+                            const int chunk = (cc & 1) * 4 + c8;               // 16-byte chunk index within the 64-key atom
+                            *reinterpret_cast<uint4*>(spa + ((chunk ^ (row & 7)) << 4)) = w;
+                        }
+                    }
+                    return ored;
+                };
+                float corr = 1.f;
+                if (!dead) {
+                    if (j == 0) m = row_max();
+                    mbar_wait(&p_empty[blk], (g & 1) ^ 1);
+                    const uint32_t ored = exp_pass(fmaf(-m, p.scale_log2, -7.f));
+                    // exponent MSB of a bf16 half set  <=>  p * 2^-7 >= 2 (or inf / NaN): the reference is stale for that row
+                    if (j > 0 && __any_sync(0xffffffffu, (ored & 0x40004000u) != 0)) {
+                        const float m_new = fmaxf(m, row_max());
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(corr) : "f"((m - m_new) * p.scale_log2));
+                        m = m_new;
+                        exp_pass(fmaf(-m, p.scale_log2, -7.f));
+                    }
+                } else {
+                    mbar_wait(&p_empty[blk], (g & 1) ^ 1);
                 }
                 tc_fence_before();
                 mbar_arrive(&s_empty[blk]);
                 fence_proxy_async();
                 mbar_arrive(&p_full[blk]);
-                l = l * corr + rs;
-                if (j > 0) take_o(o, corr_prev, g - 1);
+                if (j > 0) take_o(o, l, corr_prev, g - 1);
                 corr_prev = corr;
             }
-            take_o(o, corr_prev, g - 1);
-            const float inv = 1.f / l;
+            take_o(o, l, corr_prev, g - 1);
+            const float inv = 1.f / (C::TAIL ? o[DH < C::OCOLS ? DH : 0] : l);
             const int q = (pr * 2 + blk) * C::BM + row;
             if (q < p.S) {
                 __nv_bfloat16* dst = p.out + ((int64_t)b * p.S + q) * p.ldo + h * DH;
