@@ -88,6 +88,10 @@ int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off
 /* same contract, first-generation tcgen05 kernel (one query block per item, split-key softmax warpgroups); A/B bar */
 int vidi_attn_dense_v1(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                        int H, int dh, float scale, void* stream);
+/* same contract, second-generation kernel (ping-pong query blocks, P through shared memory); A/B bar for the current one
+ * (P and O resident in tensor memory) */
+int vidi_attn_dense_v2(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
+                       int H, int dh, float scale, void* stream);
 /* same contract, always the warp-level mma.sync kernel (generic strides / head dims; kept as the A/B bar for the tcgen05 path) */
 int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                         int H, int dh, float scale, void* stream);

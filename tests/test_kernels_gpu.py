@@ -250,7 +250,7 @@ def test_embed_gather_and_pos_split():
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("impl", ["auto", "v1", "mma"])
+@pytest.mark.parametrize("impl", ["auto", "v1", "v2", "mma"])
 @pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (1, 100, 2, 72), (2, 64, 2, 64), (5, 729, 16, 72),
                                       (1, 129, 1, 72), (3, 257, 3, 64)])
 def test_attn_dense(B, S, H, dh, impl):
@@ -265,7 +265,8 @@ def test_attn_dense(B, S, H, dh, impl):
 
 @pytest.mark.parametrize("S,H,dh,mode", [(729, 4, 72, "rising"), (1500, 4, 64, "rising"), (729, 4, 72, "falling"),
                                          (700, 2, 64, "spiky")])
-def test_attn_dense_reference_moves(S, H, dh, mode):
+@pytest.mark.parametrize("impl", ["auto", "v2"])
+def test_attn_dense_reference_moves(S, H, dh, mode, impl):
     """Score ranges that drift by far more than 2^8 between key tiles: exercises the lazy re-referencing of the
     ping-pong softmax (attn2_sm100.cu) both ways (reference must move / must not move)."""
     from vidi_b200 import ops
@@ -282,7 +283,7 @@ def test_attn_dense_reference_moves(S, H, dh, mode):
     qkv[:, d:2 * d] *= gain[:, None]
     qkv[:, :d] = qkv[:, :d].abs()                    # positive q·k drift: |q|·k with k scaled → wide logit range
     qkv = qkv.to(BF)
-    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5)
+    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, impl=impl)
     q, k, v = [t.float().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1)]
     ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, d)
     assert torch.isfinite(out.float()).all()

@@ -65,7 +65,8 @@ def dense_case(B, S, H, dh):
     fl = 4.0 * B * H * S * S * dh
     t_m = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="mma"))
     t_1 = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="v1"))
-    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), v1_tflops=round(fl / t_1 / 1e9, 1), mma_ms=round(t_m, 4),
+    t_2 = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="v2"))
+    rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), v1_tflops=round(fl / t_1 / 1e9, 1), v2_tflops=round(fl / t_2 / 1e9, 1), mma_ms=round(t_m, 4),
                mma_tflops=round(fl / t_m / 1e9, 1))
     try:
         from flash_attn import flash_attn_func

@@ -241,13 +241,13 @@ def cast_bf16(x):
 
 
 def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None, impl: str = "auto"):
-    """qkv [B*S, 3*H*dh] with Q|K|V sections -> out [B*S, H*dh].  impl: "auto" (tcgen05 for dh 64/72) | "mma"."""
+    """qkv [B*S, 3*H*dh] with Q|K|V sections -> out [B*S, H*dh].  impl: "auto" (tcgen05 for dh 64/72) | "v1" | "v2" (earlier tcgen05 generations) | "mma"."""
     L = _lib.load()
     d = H * dh
     assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
     if out is None:
         out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
-    fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense_v1 if impl == "v1" else L.vidi_attn_dense
+    fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense_v1 if impl == "v1" else L.vidi_attn_dense_v2 if impl == "v2" else L.vidi_attn_dense
     _lib.check(fn(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale, _stream()),
                "attn_dense")
     return out
