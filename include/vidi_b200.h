@@ -49,6 +49,19 @@ int vidi_gemm_bf16_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, 
                         const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
                         int out_fp32, int glu, int block_n, void* stream);
 
+/* CTA-pair GEMM with a LayerNorm folded in and/or row statistics out — the pre-LN blocks of the towers (HF SiglipEncoderLayer:
+ * layer_norm1 -> self_attn, layer_norm2 -> mlp; WhisperEncoderLayer likewise) without a LayerNorm pass over HBM:
+ *   ln_stats != NULL: A is the RAW residual stream x [M,K]; W must be pre-multiplied by gamma (W' = W diag(gamma)), ln_colsum[n] =
+ *     sum_k W'[n,k], bias must already include W beta; the epilogue computes rstd*(acc - mean*ln_colsum) + bias per row, with the
+ *     row's (sum, sumsq) given as ln_parts partial pairs: ln_stats is float [M, ln_parts, 2];
+ *   stats_out != NULL: float [M, 2*ceil(N/block_n), 2] receives the per-row (sum, sumsq) of the bf16 values stored to C, one pair
+ *     per (column tile, column half) — the ln_stats input of the GEMM that consumes C as its LayerNorm-ed operand.
+ * bf16 output, no GLU; other arguments as vidi_gemm_bf16. */
+int vidi_gemm_bf16_2cta_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                           const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                           int block_n, const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                           float* stats_out, void* stream);
+
 /* y = x_hat(x,eps) * (add_one ? 1+w : w) * out_scale.  Gemma2RMSNorm (gemma.py:107-111,162,184) / vidi RMSNorm (mm_layer/norm.py:17-25) */
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream);

@@ -64,6 +64,25 @@ def test_prefill_mini_config1_shape():
     run_case(vidi15_mini(), n_frames=8, n_chunks=1, n_text=24)
 
 
+def test_ln_fold_matches_default():
+    """Optional tower path with both LayerNorms folded into the consuming GEMMs (engine.enable_ln_fold): tower outputs agree with
+    the default LayerNorm-kernel path and with the fp32 oracle."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_mini
+    cfg = vidi15_mini()
+    sd, eng = build(cfg)
+    ids, images, mels, asz = synth.make_inputs(cfg, 5, 2, n_text=8)
+    img = images.to(BF).cuda().flatten(0, 1) if images.dim() == 5 else images.to(BF).cuda()
+    mel = mels.to(BF).cuda().flatten(0, 1) if mels.dim() == 4 else mels.to(BF).cuda()
+    v0, a0 = eng.siglip(img).float(), eng.whisper(mel).float()
+    eng.enable_ln_fold(True)
+    v1, a1 = eng.siglip(img).float(), eng.whisper(mel).float()
+    eng.enable_ln_fold(False)
+    assert rel(v1, v0) < 1.5e-2 and rel(a1, a0) < 1.5e-2, (rel(v1, v0), rel(a1, a0))
+    ref_v = R.siglip_tower(sd, cfg, img.float().cpu())
+    assert rel(v1, ref_v.reshape(v1.shape)) < 2.5e-2, rel(v1, ref_v.reshape(v1.shape))
+
+
 def test_prefill_mini_resized_featuremap():
     """Force the > max_image_tokens branch (bilinear shrink, utils.py:152-171) with a small cap."""
     import dataclasses

@@ -121,3 +121,21 @@ def test_postprocess_matches_ask_arithmetic():
     assert format_time_ranges("0.01-0.02", 25.0) == "00:00:00-00:00:00"
     assert format_time_ranges("no ranges here", 100.0) == ""
     assert build_question("a dog running.") == "<image>\nDuring which time segments in the video can we see a dog running?"
+
+
+def test_fold_layernorm_algebra():
+    """weights.fold_layernorm: rstd * (x W'^T - mean * colsum(W')) + b'  ==  Linear(LayerNorm(x))  (what gemm_ln's epilogue applies)."""
+    import torch
+    import torch.nn.functional as F
+    from vidi_b200.weights import fold_layernorm
+    g = torch.Generator().manual_seed(5)
+    M, D, N = 37, 96, 40
+    x = torch.randn(M, D, generator=g) * 2 + 1.5
+    w = (torch.randn(N, D, generator=g) * 0.1).to(torch.bfloat16); b = torch.randn(N, generator=g)
+    gamma = 1 + 0.2 * torch.randn(D, generator=g); beta = 0.3 * torch.randn(D, generator=g)
+    wp, cs, bp = fold_layernorm(w, b, gamma, beta)
+    assert wp.dtype == torch.bfloat16 and cs.dtype == torch.float32 and bp.dtype == torch.float32
+    mean = x.mean(1, keepdim=True); rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-6)
+    y = rstd * (x @ wp.float().t() - mean * cs[None, :]) + bp
+    ref = F.layer_norm(x, (D,), gamma, beta, 1e-6) @ w.float().t() + b
+    assert float((y - ref).norm() / ref.norm()) < 4e-3          # only the bf16 rounding of W*gamma differs

@@ -66,6 +66,36 @@ def test_gemm_2cta_glu():
     assert out.shape == (M, I) and rel_err(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("M,D,N,act", [(1000, 1152, 3456, 0), (700, 1152, 4304, 2), (300, 288, 520, 1), (129, 1280, 5120, 1),
+                                       (2600, 256, 768, 0)])
+def test_gemm_layernorm_fold(M, D, N, act):
+    """Pre-LN block without a LayerNorm kernel: GEMM 1 (+bias +residual) writes x and its row statistics, GEMM 2 consumes the raw x
+    with gamma/beta folded into its weights and applies mean / rstd in the epilogue  ==  Linear(LayerNorm(x))."""
+    from vidi_b200 import ops
+    from vidi_b200.weights import fold_layernorm
+    K0 = 320
+    a = rnd(M, K0, seed=61).to(BF); w0 = rnd(D, K0, scale=0.06, seed=62).to(BF)
+    b0 = rnd(D, seed=63).float(); res = (rnd(M, D, seed=64) * 2 + 0.7).to(BF)          # non-zero row means
+    st = torch.full((M, ops.ln_stats_parts(D), 2), float("nan"), device="cuda")
+    x = ops.gemm_ln(a, w0, bias=b0, residual=res, stats=st)
+    x_ref = (a.float() @ w0.float().t() + b0 + res.float())
+    assert rel_err(x, x_ref) < 6e-3
+    xs = x.float()
+    assert torch.allclose(st[..., 0].sum(1), xs.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[..., 1].sum(1), (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+    gamma = (1 + rnd(D, scale=0.2, seed=65)).float(); beta = rnd(D, scale=0.3, seed=66).float()
+    w = rnd(N, D, scale=0.05, seed=67).to(BF); b = rnd(N, seed=68).float()
+    wp, cs, bp = fold_layernorm(w, b, gamma, beta)
+    st2 = torch.empty(M, ops.ln_stats_parts(N), 2, device="cuda")
+    y = ops.gemm_ln(x, wp, bias=bp, act=act, ln=(st, cs, 1e-6), stats=st2)
+    h = F.layer_norm(xs, (D,), gamma, beta, 1e-6)
+    ref = h @ w.float().t() + b
+    if act == 1: ref = F.gelu(ref)
+    elif act == 2: ref = F.gelu(ref, approximate="tanh")
+    assert rel_err(y, ref) < 8e-3, rel_err(y, ref)
+    assert torch.allclose(st2[..., 0].sum(1), y.float().sum(1), rtol=1e-3, atol=5e-2)
+
+
 @pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
 def test_gemm_epilogues(act):
     from vidi_b200 import ops

@@ -9,6 +9,8 @@ namespace vb {
 const char* last_error();
 int gemm_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
               int, int, float, int, int, int, cudaStream_t);
+int gemm2_bf16_ln(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
+                  int, int, float, int, int, int, const float*, int, const float*, float, float*, cudaStream_t);
 int gemm2_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
                int, int, float, int, int, int, cudaStream_t);
 int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, int, float, cudaStream_t);
@@ -65,6 +67,13 @@ int vidi_gemm_bf16_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, 
                         int out_fp32, int glu, int block_n, void* stream) {
     return COUNT(vb::gemm2_bf16(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, out_fp32, glu,
                                 block_n, ST(stream)));
+}
+int vidi_gemm_bf16_2cta_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                           const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param,
+                           int block_n, const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                           float* stats_out, void* stream) {
+    return COUNT(vb::gemm2_bf16_ln(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, 0, 0, block_n,
+                                   ln_stats, ln_parts, ln_colsum, ln_eps, stats_out, ST(stream)));
 }
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream) {

@@ -229,9 +229,10 @@ static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
 
 // same contract as gemm_bf16 (gemm_sm100.cu); block_n in {128, 256}; GLU tiles: each CTA's W half must hold whole
 // [gate | up] groups, so the packed group width is block_n/2 (see weights.pack_glu) -- handled by the caller.
-int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-               const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
-               int glu, int block_n, cudaStream_t st) {
+int gemm2_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                  const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
+                  int glu, int block_n, const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                  float* stats_out, cudaStream_t st) {
     VB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm2_bf16: empty problem");
     VB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0, "gemm2_bf16: K/lda/ldw/ldc must be multiples of 8");
     if (glu) VB_REQUIRE(N % block_n == 0, "gemm2_bf16: GLU needs N %% block_n == 0 (packed gate|up tiles)");
@@ -239,6 +240,16 @@ int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.res_mod = res_mod;
     p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu;
+    if (ln_stats || stats_out) VB_REQUIRE(!glu && !out_fp32, "gemm2_bf16_ln: LayerNorm fold / row statistics need a plain bf16 output");
+    if (ln_stats) {
+        VB_REQUIRE(ln_parts > 0 && ln_colsum != nullptr, "gemm2_bf16_ln: ln_stats needs ln_parts > 0 and ln_colsum");
+        p.ln_stats = reinterpret_cast<const float2*>(ln_stats); p.ln_parts = ln_parts; p.ln_colsum = ln_colsum;
+        p.ln_inv_k = 1.0f / (float)K; p.ln_eps = ln_eps;
+    }
+    if (stats_out) {
+        p.stats_out = reinterpret_cast<float2*>(stats_out);
+        p.stats_parts = 2 * ((N + block_n - 1) / block_n);
+    }
     {   // pair-blocks (256 rows) per L2-resident group, same 48 MB budget as the 1-CTA kernel
         const int64_t per_block = (int64_t)2 * g2::BLOCK_M * K * 2;
         int64_t gm = (48ll << 20) / per_block;
@@ -248,6 +259,13 @@ int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
     if (block_n == 192) return g2::launch<192>(A, lda, W, ldw, p, st);
     if (block_n == 128) return g2::launch<128>(A, lda, W, ldw, p, st);
     VB_REQUIRE(false, "gemm2_bf16: unsupported block_n %d", block_n);
+}
+
+int gemm2_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+               const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
+               int glu, int block_n, cudaStream_t st) {
+    return gemm2_bf16_ln(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, out_fp32, glu, block_n,
+                         nullptr, 0, nullptr, 0.f, nullptr, st);
 }
 
 }  // namespace vb

@@ -22,6 +22,16 @@ struct GemmParams {
     int out_fp32;
     int glu;
     int group_m;
+    // LayerNorm folded into this GEMM (pre-LN transformer blocks of the towers): A holds the raw residual stream x, W was
+    // pre-multiplied by gamma, and the epilogue applies  out = rstd*(acc - mean*colsum) + bias'  per row, with (sum, sumsq) of
+    // each row of x given as ln_parts partial pairs written by the GEMM that produced x (stats_out below).
+    const float2* ln_stats = nullptr;
+    int ln_parts = 0;
+    const float* ln_colsum = nullptr;    // [N]: sum_k W'[n,k]
+    float ln_inv_k = 0.f, ln_eps = 0.f;
+    // per-row (sum, sumsq) of the bf16 values this GEMM stores, one pair per (column tile, column half): [M, 2*num_n_tiles]
+    float2* stats_out = nullptr;
+    int stats_parts = 0;
 };
 
 // taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;
@@ -68,6 +78,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         }
     } else {
         const int col0 = n_blk * BLOCK_N;
+        float ln_a = 1.f, ln_b = 0.f;                       // folded LayerNorm: v = ln_a * acc - ln_b * colsum
+        if (p.ln_stats) {
+            float s1 = 0.f, s2 = 0.f;
+            if (row_ok) {
+                const float2* sp = p.ln_stats + (int64_t)row * p.ln_parts;
+#pragma unroll 4
+                for (int i = 0; i < p.ln_parts; ++i) {
+                    const float2 t = sp[i];
+                    s1 += t.x; s2 += t.y;
+                }
+            }
+            const float mean = s1 * p.ln_inv_k;
+            ln_a = rsqrtf(fmaxf(s2 * p.ln_inv_k - mean * mean, 0.f) + p.ln_eps);
+            ln_b = ln_a * mean;
+        }
+        float so1 = 0.f, so2 = 0.f;                         // row statistics of what this thread stores
         // The residual row segment of chunk c+1 is requested before chunk c is processed, so its HBM latency overlaps the
         // TMEM load + math + stores of the current chunk instead of serialising four ~1 us round trips per tile.
         const __nv_bfloat16* res_row =
@@ -96,6 +122,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 const bool full = cbase + 32 <= p.N;
+                if (p.ln_stats) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 cs = *reinterpret_cast<const float4*>(p.ln_colsum + cbase + j);
+                            v[j] = ln_a * v[j] - ln_b * cs.x; v[j + 1] = ln_a * v[j + 1] - ln_b * cs.y;
+                            v[j + 2] = ln_a * v[j + 2] - ln_b * cs.z; v[j + 3] = ln_a * v[j + 3] - ln_b * cs.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) v[j] = ln_a * v[j] - ln_b * p.ln_colsum[cbase + j];
+                    }
+                }
                 if (p.bias) {
                     if (full) {
 #pragma unroll
@@ -153,17 +192,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + cbase;
                     if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(dst + j) =
-                                make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                           pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 q = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                       pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                            *reinterpret_cast<uint4*>(dst + j) = q;
+                            if (p.stats_out) {                           // statistics of the ROUNDED values (what the next LN sees)
+                                float2 f;
+                                f = unpack_bf16(q.x); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
+                                f = unpack_bf16(q.y); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
+                                f = unpack_bf16(q.z); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
+                                f = unpack_bf16(q.w); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
+                            }
+                        }
                     } else {
                         #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = __float2bfloat16(v[j]);
+                        for (int j = 0; j < 32; ++j) if (cbase + j < p.N) {
+                            const __nv_bfloat16 q = __float2bfloat16(v[j]);
+                            dst[j] = q;
+                            const float f = __bfloat162float(q);
+                            so1 += f; so2 = fmaf(f, f, so2);
+                        }
                     }
                 }
             }
         }
+        if (p.stats_out && row_ok) p.stats_out[(int64_t)row * p.stats_parts + n_blk * 2 + wg] = make_float2(so1, so2);
     }
 }
 

@@ -101,13 +101,34 @@ class Vidi15Engine:
         # (profiles/r01_ab_text_overlap_{1,2}gpu.txt: +0.5 % / +2 % step time): the ~700 small kernels that slip in between the
         # persistent GEMMs delay those kernels' CTAs more than the hidden text latency is worth.  Kept off by default.
         self.overlap_text = False
+        self.fold_ln = False         # see enable_ln_fold()
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
     # ------------------------------------------------------------------------------------------
     # towers
     # ------------------------------------------------------------------------------------------
-    def _tower_layer(self, x, L, B, S, heads, dh, eps, act):
+    def enable_ln_fold(self, on: bool = True):
+        """Optional tower path without LayerNorm kernels: both LayerNorms of a pre-LN block are folded into the GEMM that consumes
+        them (weights.fold_layernorm; row statistics travel from the producing GEMM's epilogue to the consuming one's).
+        Measured NEGATIVE on B200 for these K=1152/1280 GEMMs (profiles/r01_ab_ln_fold.txt): their epilogue is already the pacing
+        stage, the extra epilogue work costs more GEMM time (+335 ms/step) than the LayerNorm passes it removes (-171 ms).
+        Kept off by default; parity-tested (tests/test_engine_gpu.py::test_ln_fold_matches_default)."""
+        if on and not hasattr(self.W.vis.layers[0], "wqkv_f"):
+            from .weights import fold_tower_layer
+            for L in list(self.W.vis.layers) + list(self.W.aud.layers):
+                fold_tower_layer(L)
+        self.fold_ln = on
+
+    def _tower_layer(self, x, st, st2, L, B, S, heads, dh, eps, act):
+        """one pre-LN encoder block, in place on x (HF SiglipEncoderLayer / WhisperEncoderLayer)."""
+        if self.fold_ln:     # st / st2: per-row (sum, sumsq) of x written by the GEMM that produced it
+            qkv = ops.gemm_ln(x, L.wqkv_f, bias=L.bqkv_f, ln=(st, L.cqkv, eps), tag="tower")
+            a = ops.attn_dense(qkv, B, S, heads, dh, dh ** -0.5)
+            ops.gemm_ln(a, L.wo, bias=L.bo, residual=x, out=x, stats=st2, tag="tower")
+            m = ops.gemm_ln(x, L.w1_f, bias=L.b1_f, act=act, ln=(st2, L.c1, eps), tag="tower")
+            ops.gemm_ln(m, L.w2, bias=L.b2, residual=x, out=x, stats=st, tag="tower")
+            return x
         h = ops.layernorm(x, L.ln1_w, L.ln1_b, eps)
         qkv = ops.gemm(h, L.wqkv, bias=L.bqkv, tag="tower")
         a = ops.attn_dense(qkv, B, S, heads, dh, dh ** -0.5)
@@ -117,15 +138,26 @@ class Vidi15Engine:
         ops.gemm(m, L.w2, bias=L.b2, residual=x, out=x, tag="tower")
         return x
 
+    def _ln_stats(self, rows: int, width: int):
+        if not self.fold_ln:
+            return None, None
+        st = torch.empty(rows, ops.ln_stats_parts(width), 2, device=self.device, dtype=torch.float32)
+        return st, torch.empty_like(st)
+
     def siglip(self, images: torch.Tensor) -> torch.Tensor:
         """images [f,3,S,S] bf16 -> hidden_states[-2] [f*P, dv]  (siglip.py:29-34)."""
         v, Wv = self.cfg.vis, self.W.vis
         f = images.shape[0]
         A = ops.patch_im2col(images, v.patch, Wv.kpad)
-        x = ops.gemm(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches, tag="vit", alg_k=3 * v.patch * v.patch)
+        st, st2 = self._ln_stats(A.shape[0], v.hidden)
+        if self.fold_ln:
+            x = ops.gemm_ln(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches, stats=st, tag="vit",
+                            alg_k=3 * v.patch * v.patch)
+        else:
+            x = ops.gemm(A, Wv.patch_w, bias=Wv.patch_b, residual=Wv.pos, res_mod=v.patches, tag="vit", alg_k=3 * v.patch * v.patch)
         del A
         for L in Wv.layers:
-            x = self._tower_layer(x, L, f, v.patches, v.heads, v.head_dim, v.eps, ops.ACT_GELU_TANH)
+            x = self._tower_layer(x, st, st2, L, f, v.patches, v.heads, v.head_dim, v.eps, ops.ACT_GELU_TANH)
         return x
 
     def whisper(self, mels: torch.Tensor) -> torch.Tensor:
@@ -137,10 +169,14 @@ class Vidi15Engine:
         del A1
         A2 = ops.whisper_im2col2(x1, c, T)
         del x1
-        x = ops.gemm(A2, Wa.conv2_w, bias=Wa.conv2_b, act=ops.ACT_GELU_ERF, residual=Wa.pos, res_mod=T // 2)
+        st, st2 = self._ln_stats(A2.shape[0], a.d_model)
+        if self.fold_ln:
+            x = ops.gemm_ln(A2, Wa.conv2_w, bias=Wa.conv2_b, act=ops.ACT_GELU_ERF, residual=Wa.pos, res_mod=T // 2, stats=st)
+        else:
+            x = ops.gemm(A2, Wa.conv2_w, bias=Wa.conv2_b, act=ops.ACT_GELU_ERF, residual=Wa.pos, res_mod=T // 2)
         del A2
         for L in Wa.layers:
-            x = self._tower_layer(x, L, c, T // 2, a.heads, a.head_dim, a.eps, ops.ACT_GELU_ERF)
+            x = self._tower_layer(x, st, st2, L, c, T // 2, a.heads, a.head_dim, a.eps, ops.ACT_GELU_ERF)
         return ops.layernorm(x, Wa.ln_w, Wa.ln_b, a.eps)
 
     def pos_table(self, name: str, rows: int, i0: int, l: int, N: int) -> torch.Tensor:

@@ -19,6 +19,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "vidi_gemm_bf16": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _p, _l, _i, _i, _f, _i, _i, _i, _p],
     "vidi_gemm_bf16_2cta": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _p, _l, _i, _i, _f, _i, _i, _i, _p],
+    "vidi_gemm_bf16_2cta_ln": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _p, _p, _l, _i, _i, _f, _i, _p, _i, _p, _f, _p, _p],
     "vidi_rmsnorm": [_p, _l, _p, _p, _l, _i, _i, _f, _i, _f, _p],
     "vidi_residual_norm": [_p, _l, _p, _l, _p, _p, _p, _l, _i, _i, _f, _i, _i, _p],
     "vidi_layernorm": [_p, _l, _p, _p, _p, _l, _i, _i, _f, _p],

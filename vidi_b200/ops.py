@@ -50,6 +50,61 @@ def pick_block_n(M: int, N: int, glu: bool = False) -> int:
     return 128 if N > 64 else 64
 
 
+def ln_block_n(N: int) -> int:
+    """column tile of the CTA-pair GEMM on the LayerNorm-folded tower sites (fixes the layout of the row-statistics buffer)"""
+    return pick_block_n(1 << 20, N)
+
+
+def ln_stats_parts(N: int) -> int:
+    """(sum, sumsq) pairs per row written by gemm_ln(..., stats=) for an N-column output"""
+    bn = ln_block_n(N)
+    return 2 * ((N + bn - 1) // bn)
+
+
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            res_mod: int = 0, act: int = ACT_NONE, out: Optional[torch.Tensor] = None, ln=None, stats: Optional[torch.Tensor] = None,
+            tag: str = "gemm", alg_k: Optional[int] = None) -> torch.Tensor:
+    """CTA-pair GEMM of a pre-LN tower block.  ln = (stats_in [M, parts, 2] fp32, colsum [N] fp32, eps): ``a`` is the raw
+    residual stream and ``w`` / ``bias`` are the gamma / beta-folded weights (weights.fold_layernorm); stats: fp32
+    [M, ln_stats_parts(N), 2] receiving the row statistics of the stored output (the next block's ``ln`` input)."""
+    L = _lib.load()
+    assert a.dtype == BF16 and w.dtype == BF16
+    M, K = a.shape
+    N, Kw = w.shape
+    assert K == Kw, (a.shape, w.shape)
+    block_n = ln_block_n(N)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=BF16)
+    assert out.shape == (M, N) and out.dtype == BF16
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    if residual is not None:
+        assert residual.dtype == BF16
+    ln_stats, ln_parts, ln_colsum, ln_eps = None, 0, None, 0.0
+    if ln is not None:
+        ln_stats, ln_colsum, ln_eps = ln
+        assert ln_stats.dtype == torch.float32 and ln_stats.dim() == 3 and ln_stats.shape[0] == M and ln_stats.shape[2] == 2
+        assert ln_stats.is_contiguous() and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
+        ln_parts = ln_stats.shape[1]
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.shape == (M, ln_stats_parts(N), 2) and stats.is_contiguous()
+    if M == 0:
+        return out
+    prof = PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = L.vidi_gemm_bf16_2cta_ln(_ptr(a), _rowmajor(a), _ptr(w), _rowmajor(w), _ptr(out), _rowmajor(out), M, N, K,
+                                  _ptr(bias), _ptr(residual), _rowmajor(residual) if residual is not None else 0, res_mod,
+                                  act, 0.0, block_n, _ptr(ln_stats), ln_parts, _ptr(ln_colsum), float(ln_eps), _ptr(stats),
+                                  _stream())
+    _lib.check(rc, "gemm_bf16_2cta_ln")
+    if prof is not None:
+        e1.record()
+        prof.append((tag, 2.0 * M * N * (alg_k if alg_k is not None else K), e0, e1))
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          res_mod: int = 0, act: int = ACT_NONE, act_param: float = 0.0, out: Optional[torch.Tensor] = None,
          out_fp32: bool = False, glu: int = GLU_NONE, block_n: Optional[int] = None, tag: str = "gemm",

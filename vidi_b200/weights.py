@@ -58,6 +58,16 @@ def load_llm_layer(sd, l: int, c, device, glu_block: int = 256, pop: bool = Fals
     return L
 
 
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """Linear(LayerNorm(x)) with the affine part of the LayerNorm folded into the linear layer:
+         y = W (gamma * xhat + beta) + b = (W diag(gamma)) xhat + (W beta + b),      xhat = (x - mean) * rstd
+       and, with W' = bf16(W diag(gamma)) applied to the RAW x by the GEMM,  y = rstd * (x W'^T - mean * colsum(W')) + b'.
+    Returns (W' bf16 [N,K], colsum fp32 [N] of the ROUNDED W', b' fp32 [N])."""
+    wf = w.float()
+    wp = (wf * gamma.float()[None, :]).to(BF16)
+    return wp, wp.float().sum(1), (b.float() + wf @ beta.float())
+
+
 def load_tower_layer(sd, p: str, device, names, pop: bool = False):
     """names: dict(ln1, ln2, attn, fc1, fc2, out) -> key stems (SigLIP and Whisper differ only in names)."""
     g = sd.pop if pop else sd.__getitem__
@@ -79,6 +89,13 @@ def load_tower_layer(sd, p: str, device, names, pop: bool = False):
     for tag, n in (("ln1", names["ln1"]), ("ln2", names["ln2"])):
         setattr(L, f"{tag}_w", _dev(g(f"{p}.{n}.weight"), device, torch.float32))
         setattr(L, f"{tag}_b", _dev(g(f"{p}.{n}.bias"), device, torch.float32))
+    return L
+
+
+def fold_tower_layer(L):
+    """adds the LayerNorm-folded copies of the q|k|v and fc1 weights used by the optional ops.gemm_ln path (engine.fold_ln)"""
+    L.wqkv_f, L.cqkv, L.bqkv_f = fold_layernorm(L.wqkv, L.bqkv, L.ln1_w, L.ln1_b)
+    L.w1_f, L.c1, L.b1_f = fold_layernorm(L.w1, L.b1, L.ln2_w, L.ln2_b)
     return L
 
 
