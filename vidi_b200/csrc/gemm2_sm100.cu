@@ -83,7 +83,7 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = r / gm;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     using C = Cfg<BLOCK_N>;
@@ -189,7 +189,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const int row = m_blk * 2 * BLOCK_M + row_in_tile;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
-            epilogue_tile<BLOCK_N>(p, taddr, row, n_blk, wg);
+            epilogue_tile<BLOCK_N, LN>(p, taddr, row, n_blk, wg);
             tc_fence_before();
             mbar_arrive_leader(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -204,7 +204,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool LN>
 static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
     using C = Cfg<BLOCK_N>;
     CUtensorMap ta, tb;
@@ -213,14 +213,14 @@ static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N / 2))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel<BLOCK_N, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
     const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int max_pairs = num_sms() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    gemm2_bf16_kernel<BLOCK_N><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
+    gemm2_bf16_kernel<BLOCK_N, LN><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -255,9 +255,15 @@ int gemm2_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
         int64_t gm = (48ll << 20) / per_block;
         p.group_m = (int)(gm < 4 ? 4 : gm > 32 ? 32 : gm);
     }
-    if (block_n == 256) return g2::launch<256>(A, lda, W, ldw, p, st);
-    if (block_n == 192) return g2::launch<192>(A, lda, W, ldw, p, st);
-    if (block_n == 128) return g2::launch<128>(A, lda, W, ldw, p, st);
+    if (ln_stats || stats_out) {          // separate instantiation: the plain kernel carries none of the LayerNorm-fold code
+        if (block_n == 256) return g2::launch<256, true>(A, lda, W, ldw, p, st);
+        if (block_n == 192) return g2::launch<192, true>(A, lda, W, ldw, p, st);
+        if (block_n == 128) return g2::launch<128, true>(A, lda, W, ldw, p, st);
+    } else {
+        if (block_n == 256) return g2::launch<256, false>(A, lda, W, ldw, p, st);
+        if (block_n == 192) return g2::launch<192, false>(A, lda, W, ldw, p, st);
+        if (block_n == 128) return g2::launch<128, false>(A, lda, W, ldw, p, st);
+    }
     VB_REQUIRE(false, "gemm2_bf16: unsupported block_n %d", block_n);
 }
 

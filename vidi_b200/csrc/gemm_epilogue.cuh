@@ -36,7 +36,7 @@ struct GemmParams {
 
 // taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;
 // wg: which half of the tile columns this warp drains; n_blk: tile column index.
-template <int BLOCK_N>
+template <int BLOCK_N, bool LN = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int n_blk, int wg) {
     const bool row_ok = row < p.M;
     const int out_cols_total = p.glu ? p.N / 2 : p.N;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     } else {
         const int col0 = n_blk * BLOCK_N;
         float ln_a = 1.f, ln_b = 0.f;                       // folded LayerNorm: v = ln_a * acc - ln_b * colsum
-        if (p.ln_stats) {
+        if (LN && p.ln_stats) {
             float s1 = 0.f, s2 = 0.f;
             if (row_ok) {
                 const float2* sp = p.ln_stats + (int64_t)row * p.ln_parts;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 const bool full = cbase + 32 <= p.N;
-                if (p.ln_stats) {
+                if (LN && p.ln_stats) {
                     if (full) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -196,7 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                             const uint4 q = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
                                                        pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
                             *reinterpret_cast<uint4*>(dst + j) = q;
-                            if (p.stats_out) {                           // statistics of the ROUNDED values (what the next LN sees)
+                            if (LN && p.stats_out) {                     // statistics of the ROUNDED values (what the next LN sees)
                                 float2 f;
                                 f = unpack_bf16(q.x); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
                                 f = unpack_bf16(q.y); so1 += f.x + f.y; so2 = fmaf(f.x, f.x, fmaf(f.y, f.y, so2));
@@ -209,14 +209,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                         for (int j = 0; j < 32; ++j) if (cbase + j < p.N) {
                             const __nv_bfloat16 q = __float2bfloat16(v[j]);
                             dst[j] = q;
-                            const float f = __bfloat162float(q);
-                            so1 += f; so2 = fmaf(f, f, so2);
+                            if (LN) {
+                                const float f = __bfloat162float(q);
+                                so1 += f; so2 = fmaf(f, f, so2);
+                            }
                         }
                     }
                 }
             }
         }
-        if (p.stats_out && row_ok) p.stats_out[(int64_t)row * p.stats_parts + n_blk * 2 + wg] = make_float2(so1, so2);
+        if (LN && p.stats_out && row_ok) p.stats_out[(int64_t)row * p.stats_parts + n_blk * 2 + wg] = make_float2(so1, so2);
     }
 }
 
