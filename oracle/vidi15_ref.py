@@ -15,10 +15,12 @@ commits the outputs of
   * DattnMMMixin.encode_video_images / encode_video_audios (on HF SiglipVisionModel / WhisperEncoder),
   * DattnGemma2DecoderLayer.forward + forward_xattn + flash_cross_attention_forward + splitted_call
     (two stacked layers, all three streams; the T2T half runs the installed HF Gemma2Attention),
-which ``tests/test_oracle_golden.py`` checks this restatement against to <= 5e-5.
-Not pinned (no runnable reference): the model-level loop DattnGemma2Model.forward (gemma.py:267-424:
-normaliser, layer loop, final norm) and lm_head + soft-cap (gemma.py:564-569) -- HF 5.x removed the
-cache classes that loop constructs; those ~10 lines are restated from the source (citations below).
+  * the whole model: DattnGemma2ForCausalLM.forward -> prepare_inputs_labels_for_multimodal -> DattnGemma2Model.forward
+    (gemma.py:267-424,484-601; multimodal.py:339-451) run unmodified with use_cache=False on instances assembled around
+    those layers: sentinel stripping, embedding, the sqrt(D) normaliser, the layer loop, final norm, lm_head, soft-cap,
+which ``tests/test_oracle_golden.py`` checks this restatement against to <= 5e-5 (logits included).
+Not exercised by the fixtures: the use_cache=True branch (HF 5.x removed the 4.50 cache classes it constructs); decode
+steps of ``greedy_generate`` therefore rest on prefill parity plus the cache-equivalence test in tests/.
 
 Everything is fp32; functions take an HF-layout ``state_dict`` (keys of SURVEY.md section 8b).
 """

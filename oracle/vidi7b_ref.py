@@ -4,12 +4,13 @@ Same rules as vidi15_ref.py (only tests / smoke / bench cpu legs may import it).
 Vidi_7B/model/lmm/dattn/mistral.py:44-116 (forward_xattn), :131-137 (feed_foward), :139-274 (decoder layer),
 :296-453 (model loop), :596-616 (lm_head, fp32 logits), Vidi_7B/model/lmm/dattn/multimodal.py:154-227 (encoders)
 and Vidi_7B/model/mm_vision/pool.py:6-26 (learned conv pool + align_corners bilinear).
-PARITY PINNING (tests/test_oracle_golden.py): the learned-conv pool is checked against the reference's Conv2DPool
-run by file path, and ``stream_layer`` + ``text_layer`` against two stacked calls of the reference's own
-DattnMistralDecoderLayer.forward / forward_xattn / flash_cross_attention_forward (tests/golden/make_golden_7b.py;
-the transformers==4.44.2 MistralFlashAttention2 base class, gone from the installed 5.5.0, and flash-attn's kernels are
-replaced there by fp32 restatements of their semantics) to <= 5e-5.  Unpinned: the encoders' composition
-(multimodal.py:154-227, restated from source; its leaf modules are pinned) and the model-level loop / lm_head.
+PARITY PINNING (tests/test_oracle_golden.py), all against the reference's own code run through tests/golden/make_golden_7b.py
+(the transformers==4.44.2 MistralFlashAttention2 base class, gone from the installed 5.5.0, and flash-attn's kernels are
+replaced there by fp32 restatements of their semantics): the learned-conv pool vs the reference's Conv2DPool; ``stream_layer``
++ ``text_layer`` vs two stacked DattnMistralDecoderLayer.forward / forward_xattn / flash_cross_attention_forward calls; and the
+WHOLE prefill vs DattnMistralForCausalLM.forward -> prepare_inputs_labels_for_multimodal / encode_video_images /
+encode_video_audios -> DattnMistralModel.forward run unmodified with use_cache=False (encoder outputs and logits) -- all to
+<= 5e-5.  Not exercised: the use_cache=True branch.
 Differences from Vidi1.5: no sqrt(D) normaliser, Mistral RMSNorm (w * x_hat, eps from config), one
 MLP norm (= post_attention_layernorm), SwiGLU, no soft-caps, scale 1/sqrt(128), diagonal update without a norm,
 residual added after summing the three attentions, learned-conv pooling to pool^2 tokens per frame, audio pool keeps

@@ -174,6 +174,7 @@ gcfg.mm_splits = 2
 from transformers.models.gemma2.modeling_gemma2 import Gemma2RotaryEmbedding  # noqa: E402
 
 layer_out = []
+ref_layers = []
 T = 6
 Himg, Haud = X_img.shape[1], X_aud.shape[1]
 ids_noimg = ids[ids != -200]
@@ -202,6 +203,7 @@ for l in range(2):
             past_key_value=None, past_image_key_value=None, past_audio_key_value=None, use_cache=False,
             cache_position=torch.arange(T))
     layer_out.append(dict(text=hs_out[0], image=im_out[0], audio=au_out[0]))
+    ref_layers.append(layer)
     hs, im, au = hs_out, im_out, au_out
 OUT["decoder"] = dict(ids=ids, H0=H0[0], img0=img0[0], aud0=aud0[0], layers=layer_out)
 
@@ -218,6 +220,47 @@ with torch.no_grad():
         m7 = _pool7.Conv2DPool(6, 6, 27, s_out).eval()
         out7[s_out] = dict(w=m7.conv.weight.data.clone(), out=m7(x7))
     OUT["pool7b"] = dict(x=x7, cases=out7)
+
+# ---------------------------------------------------------------- reference model-level loop, input prep and LM head
+# DattnGemma2Model.forward (gemma.py:267-424), DattnGemma2ForCausalLM.forward (gemma.py:484-601) and
+# DattnMMMixin.prepare_inputs_labels_for_multimodal (multimodal.py:339-451) run UNMODIFIED on instances assembled around the
+# reference layers above (the constructors want flash-attn-2 and hub downloads; forward() itself does not).  use_cache=False: the
+# HF 4.50 cache classes the cached branch builds no longer exist in 5.x.
+from transformers.models.gemma2.modeling_gemma2 import Gemma2RMSNorm  # noqa: E402
+
+mdl = G.DattnGemma2Model.__new__(G.DattnGemma2Model)
+torch.nn.Module.__init__(mdl)
+mdl.config = gcfg
+mdl.embed_tokens = torch.nn.Embedding(cfg.llm.vocab, D)
+mdl.embed_tokens.weight.data.copy_(sd["model.embed_tokens.weight"])
+mdl.layers = torch.nn.ModuleList(ref_layers)
+mdl.norm = Gemma2RMSNorm(D, eps=1e-6)
+mdl.norm.weight.data.copy_(sd["model.norm.weight"])
+mdl.rotary_emb = rot
+mdl.gradient_checkpointing = False
+for _k, _v in vars(inner).items():
+    setattr(mdl, _k, _v)
+mdl.text_tokenizer = SimpleNamespace(padding_side="right")
+top = G.DattnGemma2ForCausalLM.__new__(G.DattnGemma2ForCausalLM)
+torch.nn.Module.__init__(top)
+top.model = mdl.eval()
+top.lm_head = torch.nn.Linear(D, cfg.llm.vocab, bias=False)
+top.lm_head.weight.data.copy_(sd.get("lm_head.weight", sd["model.embed_tokens.weight"]))
+for _k, _v in dict(train_vis=False, train_aud=False, mm_splits=2, mm_image_pool_size=2, mm_audio_pool_size=5, mm_input_type="video").items():
+    setattr(gcfg, _k, _v)
+top.config = gcfg
+top.vocab_size = cfg.llm.vocab
+top.eval()
+with torch.no_grad():
+    mo = G.DattnGemma2Model.forward(
+        mdl, inputs_embeds=sd["model.embed_tokens.weight"][ids_noimg][None], attention_mask=torch.ones(1, T, dtype=torch.long),
+        image_embeds=X_img, image_attention_mask=m_img, audio_embeds=X_aud, audio_attention_mask=m_aud, use_cache=False,
+        output_attentions=False, output_hidden_states=False, return_dict=True)
+    co = G.DattnGemma2ForCausalLM.forward(
+        top, input_ids=ids[None] if ids.dim() == 1 else ids, attention_mask=torch.ones(1, ids.numel(), dtype=torch.long),
+        images=[images], audios=[mels], audio_sizes=[asz], use_cache=False,
+        output_attentions=False, output_hidden_states=False, return_dict=True)
+OUT["model"] = dict(last_hidden_state=mo.last_hidden_state[0], logits=co.logits[0].float())
 
 torch.save(OUT, os.path.join(HERE, "vidi15_reference_golden.pt"))
 sz = os.path.getsize(os.path.join(HERE, "vidi15_reference_golden.pt"))

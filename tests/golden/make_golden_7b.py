@@ -121,5 +121,113 @@ for l in range(2):
     hs, im, au = hs_out, im_out, au_out
 OUT = dict(seed=778, cfg=dict(llm=vars(cfg.llm), vis=vars(cfg.vis), aud=vars(cfg.aud), pool=cfg.mm_image_pool_size),
            H0=H[0], img0=img[0], aud0=aud[0], layers=out_layers)
+
+# ---------------------------------------------------------------- whole model: encoders + input prep + layer loop + lm_head
+# DattnMistralForCausalLM.forward (mistral.py:512-616) -> DattnMMMixin.prepare_inputs_labels_for_multimodal / encode_video_images /
+# encode_video_audios (Vidi_7B/model/lmm/dattn/multimodal.py:154-227) -> DattnMistralModel.forward (mistral.py:296-453), all run
+# UNMODIFIED on instances assembled around the reference layers above and the reference's own leaf modules (the constructors
+# want hub downloads and flash-attn; forward() does not).  Towers: installed HF SiglipVisionModel / WhisperEncoder.
+from types import SimpleNamespace  # noqa: E402
+
+from transformers import SiglipVisionConfig, SiglipVisionModel, WhisperConfig  # noqa: E402
+from transformers.models.whisper.modeling_whisper import WhisperEncoder  # noqa: E402
+from model.mm_layer import MLP, RMSNorm  # noqa: E402  (reference code)
+from model.mm_vision import Conv2DPool, LearnablePosEmbd  # noqa: E402  (reference code)
+
+D = cfg.llm.hidden
+vcfg = SiglipVisionConfig(hidden_size=32, intermediate_size=48, num_hidden_layers=3, num_attention_heads=2, image_size=378,
+                          patch_size=14, hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+vcfg._attn_implementation = "eager"
+vis = SiglipVisionModel(vcfg).eval()
+_miss = vis.load_state_dict({k[len("model.mm_vis."):]: v for k, v in sd.items() if k.startswith("model.mm_vis.")}, strict=False)
+assert all("head" in k for k in _miss.missing_keys), _miss
+acfg = WhisperConfig(d_model=32, encoder_layers=2, encoder_attention_heads=2, encoder_ffn_dim=64, num_mel_bins=128,
+                     max_source_positions=1500, activation_function="gelu")
+acfg._attn_implementation = "eager"
+aud_enc = WhisperEncoder(acfg).eval()
+aud_enc.load_state_dict({k[len("model.mm_aud.encoder."):]: v for k, v in sd.items() if k.startswith("model.mm_aud.encoder.")})
+
+
+class VisTower(nn.Module):
+    """Same contract as SiglipVisionTower.forward (Vidi_7B/model/mm_vision/siglip.py) around the HF model built above."""
+    num_patches_per_side = 27
+    hidden_size = 32
+
+    def __init__(self, m):
+        super().__init__()
+        self.vision_model = m.vision_model
+        self.m = m
+
+    def forward(self, imgs):
+        o = self.m(imgs, output_hidden_states=True)
+        return o.pooler_output, o.hidden_states[-2]
+
+
+class AudTower(nn.Module):
+    hidden_size = 32
+
+    def __init__(self, enc):
+        super().__init__()
+        self.encoder = enc
+        self.config = enc.config
+
+    def forward(self, a):
+        return self.encoder(a)[0]
+
+
+def load_mod(mod, prefix):
+    mod.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)})
+    return mod.eval()
+
+
+mdl = M.DattnMistralModel.__new__(M.DattnMistralModel)
+nn.Module.__init__(mdl)
+mdl.config = mcfg
+mdl.embed_tokens = nn.Embedding(cfg.llm.vocab, D)
+mdl.embed_tokens.weight.data.copy_(sd["model.embed_tokens.weight"])
+ref_layers = []
+for l in range(2):
+    layer = M.DattnMistralDecoderLayer(mcfg, l).eval()
+    layer.load_state_dict({k[len(f"model.layers.{l}."):]: v for k, v in sd.items() if k.startswith(f"model.layers.{l}.")})
+    ref_layers.append(layer)
+mdl.layers = nn.ModuleList(ref_layers)
+mdl.norm = load_mod(mm.MistralRMSNorm(D, eps=1e-5), "model.norm.")
+mdl.gradient_checkpointing = False
+pool_s = cfg.mm_image_pool_size
+mdl.mm_vis, mdl.mm_aud = VisTower(vis), AudTower(aud_enc)
+mdl.audio_processor = SimpleNamespace(nb_max_frames=3000)
+mdl.text_tokenizer = SimpleNamespace(padding_side="right")
+mdl.mm_rand_img_pool = load_mod(Conv2DPool(d_in=32, d_out=32, s_in=27, s_out=pool_s), "model.mm_rand_img_pool.")
+mdl.mm_rand_img_projector = load_mod(MLP("mlp2x_gelu", 32, D), "model.mm_rand_img_projector.")
+mdl.mm_rand_img_norm = load_mod(RMSNorm(D), "model.mm_rand_img_norm.")
+mdl.mm_rand_aud_pool = load_mod(nn.Conv1d(32, 32, cfg.mm_audio_pool_size, stride=cfg.mm_audio_pool_size, bias=False), "model.mm_rand_aud_pool.")
+mdl.mm_rand_aud_projector = load_mod(MLP("mlp2x_gelu", 32, D), "model.mm_rand_aud_projector.")
+mdl.mm_rand_aud_norm = load_mod(RMSNorm(D), "model.mm_rand_aud_norm.")
+mdl.mm_rand_llm_norm = load_mod(RMSNorm(D), "model.mm_rand_llm_norm.")
+mdl.mm_rand_pos_h = load_mod(LearnablePosEmbd(D, pool_s), "model.mm_rand_pos_h.")
+mdl.mm_rand_pos_w = load_mod(LearnablePosEmbd(D, pool_s), "model.mm_rand_pos_w.")
+mdl.mm_rand_pos_t = load_mod(LearnablePosEmbd(D, cfg.mm_time_interval), "model.mm_rand_pos_t.")
+top = M.DattnMistralForCausalLM.__new__(M.DattnMistralForCausalLM)
+nn.Module.__init__(top)
+top.model = mdl.eval()
+top.lm_head = nn.Linear(D, cfg.llm.vocab, bias=False)
+top.lm_head.weight.data.copy_(sd["lm_head.weight"])
+for _k, _v in dict(train_vis=False, train_aud=False, mm_splits=2, mm_image_pool_size=pool_s, mm_audio_pool_size=cfg.mm_audio_pool_size,
+                   mm_input_type="video", loss_thres=None).items():
+    setattr(mcfg, _k, _v)
+top.config = mcfg
+top.vocab_size = cfg.llm.vocab
+top.eval()
+ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=98, audio_size=1234)
+with torch.no_grad():
+    X_img, m_img2 = top.encode_video_images([images])
+    X_aud, m_aud2 = top.encode_video_audios([mels], [asz])
+    co = M.DattnMistralForCausalLM.forward(
+        top, input_ids=ids[None] if ids.dim() == 1 else ids, attention_mask=torch.ones(1, ids.numel(), dtype=torch.long),
+        images=[images], audios=[mels], audio_sizes=[asz], use_cache=False,
+        output_attentions=False, output_hidden_states=False, return_dict=True)
+OUT["model"] = dict(inputs="synth.make_inputs(cfg, 3, 1, n_text=6, seed=98, audio_size=1234)", audio_size=asz,
+                    image_embeds=X_img[0], image_mask=m_img2[0], audio_embeds=X_aud[0], audio_mask=m_aud2[0],
+                    logits=co.logits[0].float())
 torch.save(OUT, os.path.join(HERE, "vidi7b_reference_golden.pt"))
 print("wrote vidi7b_reference_golden.pt", os.path.getsize(os.path.join(HERE, "vidi7b_reference_golden.pt")), "bytes")

@@ -99,6 +99,20 @@ def test_prefill_consistency_with_layer_fixture():
     assert logits.shape == (6, cfg.llm.vocab) and float(logits.abs().max()) <= 30.0
 
 
+def test_prefill_logits_match_reference_model_forward():
+    """End to end against the reference's own DattnGemma2ForCausalLM.forward -> prepare_inputs_labels_for_multimodal ->
+    DattnGemma2Model.forward (gemma.py:267-424,484-601; multimodal.py:339-451) run unmodified on the same seeded tiny model:
+    sentinel stripping, embedding, normaliser, the 3-stream layer loop, final norm, lm_head and the 30*tanh(x/30) soft-cap."""
+    cfg = tiny_cfg()
+    sd = synth.make_state_dict(cfg, seed=G["seed"])
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=99, audio_size=1234)
+    logits, inter = R.prefill(sd, cfg, ids, images, mels, asz, return_intermediates=True)
+    close(logits, G["model"]["logits"], 5e-5)
+    assert torch.equal(logits.argmax(-1), G["model"]["logits"].argmax(-1))
+    if "final_hidden" in inter:
+        close(inter["final_hidden"], G["model"]["last_hidden_state"], 5e-5)
+
+
 def test_vidi7b_conv_pool_matches_reference():
     """Vidi_7B/model/mm_vision/pool.py Conv2DPool (learned conv + align_corners bilinear), run from the reference file."""
     from oracle import vidi7b_ref as R7
@@ -136,3 +150,22 @@ def test_vidi7b_decoder_layers_match_reference_layer_forward():
         H = R7.text_layer(H, sd, p, cfg, cos, sin, [(Ki, Vi, ones_i), (Ka, Va, ones_a)])
         S_img, S_aud = S_img2, S_aud2
         close(S_img, ref["image"], 5e-5); close(S_aud, ref["audio"], 5e-5); close(H, ref["text"], 5e-5)
+
+
+def test_vidi7b_prefill_matches_reference_model_forward():
+    """Vidi-7B end to end against the reference's own DattnMistralForCausalLM.forward -> prepare_inputs_labels_for_multimodal /
+    encode_video_images / encode_video_audios (Vidi_7B/model/lmm/dattn/multimodal.py:154-227) -> DattnMistralModel.forward
+    (mistral.py:296-453,512-616), run unmodified (tests/golden/make_golden_7b.py): encoder composition, learned-conv pooling,
+    input prep, layer loop, final norm, untied lm_head with fp32 logits."""
+    from oracle import vidi7b_ref as R7
+    from vidi_b200.config import MistralCfg, Vidi7BConfig
+    G7 = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vidi7b_reference_golden.pt"), weights_only=False)
+    c, g = G7["cfg"], G7["model"]
+    cfg = Vidi7BConfig(llm=MistralCfg(**c["llm"]), vis=VisionCfg(**c["vis"]), aud=AudioCfg(**c["aud"]), mm_image_pool_size=c["pool"])
+    sd = synth.make_state_dict(cfg, seed=G7["seed"])
+    ids, images, mels, asz = synth.make_inputs(cfg, 3, 1, n_text=6, seed=98, audio_size=g["audio_size"])
+    logits, inter = R7.prefill(sd, cfg, ids, images, mels, asz, return_intermediates=True)
+    close(inter["image_embeds"], g["image_embeds"], 5e-5)
+    close(inter["audio_embeds"], g["audio_embeds"], 5e-5)
+    close(logits, g["logits"], 5e-5)
+    assert torch.equal(logits.argmax(-1), g["logits"].argmax(-1))
