@@ -1,5 +1,7 @@
-"""Timing probes for the tower attention kernel (not a benchmark): per-item vs per-tile cost, and what each pipeline stage
-costs (VIDI_ATTN_DBG bits disable parts of the kernel; results are then wrong by design)."""
+"""Timing probes for the tower attention kernel (not a benchmark): cost per work item and per 128-key tile over a sweep of sequence
+lengths.  During the v2 -> v3 work the kernel also had a VIDI_ATTN_DBG switch that disabled single pipeline stages (exp2, P V MMAs,
+S loads, P store ...; results wrong by design) — those hooks are gone from the product kernel; the raw numbers they produced are in
+profiles/r01_attn_probes_raw.txt (the `dbg` column is therefore always 0 now)."""
 import json, os, sys, subprocess
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -15,8 +15,6 @@
 //   TMEM: block A S/P buffers [0,64) [64,128), block B [128,192) [192,256), O_A [256,336), O_B [384,464).
 // Q K(j+2)^T overwrites the buffer P(j) V(j) reads; it is issued after it by the same thread (the tensor pipe executes one
 // thread's MMAs in issue order).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace vb {
@@ -50,7 +48,6 @@ struct Fa3Params {
     float scale_log2;
     __nv_bfloat16* out;
     int64_t ldo;
-    int dbg;                 // timing probe only (VIDI_ATTN_DBG): 64 = no K/V TMA loads
 };
 
 // D[tmem] (+)= A[tmem] * B[smem]: A is M x 16 bf16, row i in TMEM lane i, elements (2c, 2c+1) packed in 32-bit column c
@@ -158,7 +155,6 @@ attn_fwd3_sm100_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gr
                     for (int j = 0; j < nkt; ++j, ++g) {
                         const int st = g % KV;
                         mbar_wait(&kv_empty[st], ((g / KV) & 1) ^ 1);
-                        if (p.dbg & 64) { mbar_arrive(&kv_full[st]); continue; }
                         mbar_expect_tx(&kv_full[st], 2 * C::kKBytes);
                         uint8_t* sk = smem + C::kOffK + st * C::kKSlot;
                         uint8_t* sv = smem + C::kOffV + st * C::kKSlot;
@@ -432,8 +428,6 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     p.scale_log2 = scale * kLog2eC;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
-    const char* dbg = getenv("VIDI_ATTN_DBG");
-    p.dbg = dbg ? atoi(dbg) : 0;
     const int grid = p.items < num_sms() ? p.items : num_sms();
     attn_fwd3_sm100_kernel<DH><<<grid, 384, C::kSmem, st>>>(tm_q_main, tm_q_tail, tm_k_main, tm_k_tail, p);
     VB_CUDA_CHECK(cudaGetLastError());
