@@ -1,0 +1,97 @@
+"""Host-side pre-processing against the third-party pieces the reference calls: Pillow's BICUBIC resize
+(bit-exact) and the installed HF SiglipImageProcessor / WhisperFeatureExtractor."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from vidi_b200.preprocess import (SiglipImageProcessorLite, WhisperFeatureExtractorLite, mel_filter_bank, resize_bicubic_u8,
+                                  sample_frame_indices)
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(270, 480, 384, 384), (720, 1280, 384, 384), (384, 384, 384, 384), (100, 60, 384, 384),
+                                       (1080, 1920, 384, 384), (37, 41, 16, 50), (500, 384, 384, 384), (384, 777, 384, 384)])
+def test_resize_is_bit_exact_pillow_bicubic(h, w, oh, ow):
+    """integer restatement of libImaging/Resample.c == PIL.Image.resize(..., BICUBIC) on every byte (img_utils.py:182-185)."""
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[: h // 3] = (img[: h // 3] // 64) * 64                      # flat / blocky areas and hard edges as well as noise
+    img[:, : w // 4, 1] = 255
+    ref = np.asarray(Image.fromarray(img).convert("RGB").resize((ow, oh), resample=Image.BICUBIC))
+    out = resize_bicubic_u8(torch.from_numpy(img), oh, ow).numpy()
+    assert out.shape == ref.shape and out.dtype == np.uint8
+    assert np.array_equal(out, ref), int(np.abs(out.astype(int) - ref.astype(int)).max())
+
+
+def test_resize_batched_frames_equal_per_frame():
+    rng = np.random.default_rng(3)
+    frames = torch.from_numpy(rng.integers(0, 256, (5, 90, 160, 3), dtype=np.uint8))
+    out = resize_bicubic_u8(frames, 48, 48)
+    for f in range(5):
+        ref = np.asarray(Image.fromarray(frames[f].numpy()).resize((48, 48), resample=Image.BICUBIC))
+        assert np.array_equal(out[f].numpy(), ref)
+
+
+def test_image_processor_matches_reference_resize_branch():
+    """process_images 'resize' branch: PIL resize to output_size, then HF SiglipImageProcessor.preprocess (img_utils.py:181-187)."""
+    from transformers import SiglipImageProcessor
+    hf = SiglipImageProcessor(size={"height": 384, "width": 384}, resample=3, do_rescale=True, rescale_factor=1 / 255, do_normalize=True,
+                              image_mean=[0.5] * 3, image_std=[0.5] * 3)
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (3, 240, 426, 3), dtype=np.uint8)
+    ref = []
+    for f in frames:
+        im = Image.fromarray(f).convert("RGB").resize((384, 384), resample=Image.BICUBIC)
+        ref.append(hf.preprocess(im, return_tensors="pt")["pixel_values"][0])
+    ref = torch.stack(ref)
+    out = SiglipImageProcessorLite(384).preprocess(torch.from_numpy(frames))
+    assert out.shape == ref.shape == (3, 3, 384, 384) and out.dtype == torch.float32
+    assert float((out - ref).abs().max()) <= 1e-6
+
+
+def test_mel_filter_bank_matches_hf():
+    from transformers.audio_utils import mel_filter_bank as hf_fb
+    ref = hf_fb(num_frequency_bins=201, num_mel_filters=128, min_frequency=0.0, max_frequency=8000.0, sampling_rate=16000,
+                norm="slaney", mel_scale="slaney")
+    out = mel_filter_bank(201, 128, 16000).numpy()
+    assert out.shape == ref.shape and np.abs(out - ref).max() <= 1e-9
+
+
+@pytest.mark.parametrize("seconds", [7.3, 30.0, 61.7])
+def test_log_mel_matches_hf_feature_extractor(seconds):
+    """process_audio (vid_utils.py:52-63): 30-s chunks -> WhisperFeatureExtractor features and audio_size = sum floor(len/160)."""
+    from transformers import WhisperFeatureExtractor
+    fe = WhisperFeatureExtractor(feature_size=128)
+    rng = np.random.default_rng(int(seconds * 10))
+    n = int(seconds * 16000)
+    t = np.arange(n) / 16000.0
+    audio = (0.3 * np.sin(2 * np.pi * 440 * t) * (t % 3 < 2) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    chunks = [audio[i:i + fe.n_samples] for i in range(0, n, fe.n_samples)]
+    ref = fe(chunks, sampling_rate=16000, return_tensors="pt")["input_features"]
+    feats, size = WhisperFeatureExtractorLite(128)(torch.from_numpy(audio))
+    assert feats.shape == ref.shape and feats.dtype == torch.float32
+    assert float((feats - ref).abs().max()) <= 1e-4, float((feats - ref).abs().max())
+    assert size == sum(len(c) // 160 for c in chunks)
+
+
+def test_sample_frame_indices_follow_load_video():
+    assert sample_frame_indices(300, 29.97) == list(range(0, 300, 30))
+    assert sample_frame_indices(100, 24.0, fps=2.0) == list(range(0, 100, 12))
+
+
+def test_processors_accept_the_reference_call_pattern():
+    """the way process_images / process_audio call them (img_utils.py:180-187, vid_utils.py:52-63): PIL image in, dict out;
+    list of numpy chunks in, object with .input_features / .num_frames out."""
+    rng = np.random.default_rng(5)
+    ip, ap = SiglipImageProcessorLite(384), WhisperFeatureExtractorLite(128)
+    pil = Image.fromarray(rng.integers(0, 256, (120, 200, 3), dtype=np.uint8))
+    image = pil.resize((ip.output_size, ip.output_size), resample=Image.BICUBIC)
+    px = ip.preprocess(image, return_tensors="pt")["pixel_values"][0]
+    direct = ip.preprocess(torch.from_numpy(np.asarray(pil))[None])[0]
+    assert px.shape == (3, 384, 384) and torch.equal(px, direct)
+    audio = (0.1 * rng.standard_normal(16000 * 41)).astype(np.float32)
+    chunks = [audio[i:i + ap.n_samples] for i in range(0, len(audio), ap.n_samples)]
+    out = ap(chunks, sampling_rate=ap.sampling_rate, return_tensors="pt", return_token_timestamps=True)
+    feats, size = ap(torch.from_numpy(audio))
+    assert int(out.num_frames.sum()) == size == len(audio) // 160
+    assert out.input_features.shape == (2, 128, 3000) and torch.equal(out.input_features, feats)
