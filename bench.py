@@ -34,6 +34,8 @@ WORKLOADS = {
     "c2p": (600, 20, 32, "Vidi1.5-9B 10-min synthetic video, 66k tokens (BASELINE config 2')"),
     "c2": (80, 3, 32, "Vidi1.5-9B 80-frame synthetic video, 16.5k tokens (BASELINE config 2)"),
     "c1": (8, 1, 32, "Vidi1.5-9B 8-frame plumbing case (BASELINE config 1)"),
+    # config 5: the repo has no bbox head, the "STG" run is the same prefill path on a 30-min video
+    "c5": (1800, 60, 32, "Vidi1.5-9B 30-min synthetic video, 63k tokens (BASELINE config 5, same path)"),
     # Vidi-7B: per clip 300 frames / 10 chunks; a step = 8 clips back to back (BASELINE config 4, mm_image_pool_size=16 assumed)
     "c4": (300, 10, 32, "Vidi-7B batch 8 x 5-min synthetic clips, 8 x (76.8k image + 3k audio) tokens (BASELINE config 4)"),
 }
