@@ -94,6 +94,17 @@ int vidi_sinusoid_split(const float* div_term, void* out, int rows, int i0, int 
 int vidi_split3(const float* x, void* out, int64_t rows, int D, int mode, void* stream);
 int vidi_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 
+/* frame pre-processing: the two passes of PIL.Image.resize(..., BICUBIC) as process_images' 'resize' branch applies it
+ * (vidi/dataset/img_utils.py:181-187; Pillow libImaging/Resample.c 8-bit path), bit-exact integer arithmetic.  Tap tables from the host
+ * (precompute_coeffs + normalize_coeffs_8bpc): xmin int32 [out_size], kk int32 [out_size, ksize] (22-bit fixed point).
+ *   vidi_resample_u8:             src uint8 [outer, in_size, inner] -> dst uint8 [outer, out_size, inner]   (horizontal pass: inner = 3)
+ *   vidi_resample_u8_to_chw_bf16: src uint8 [F, in_h, W, 3] -> dst bf16 [F, 3, out_h, W] = ((v * rescale) - mean) / std   (vertical pass
+ *                                 fused with the SiglipImageProcessor affine and the HWC -> CHW change) */
+int vidi_resample_u8(const uint8_t* src, uint8_t* dst, int64_t outer, int in_size, int out_size, int inner, const int32_t* xmin,
+                     const int32_t* kk, int ksize, void* stream);
+int vidi_resample_u8_to_chw_bf16(const uint8_t* src, void* dst, int F, int in_h, int out_h, int W, const int32_t* ymin,
+                                 const int32_t* kk, int ksize, float rescale, float mean, float stdv, void* stream);
+
 /* attention */
 /* bidirectional flash attention for the towers (flash_attn_func via HF SiglipAttention / WhisperAttention), K3/K8 */
 int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,

@@ -14,6 +14,8 @@ int gemm2_bf16_ln(const void*, int64_t, const void*, int64_t, void*, int64_t, in
 int gemm2_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, const float*, const void*, int64_t,
                int, int, float, int, int, int, cudaStream_t);
 int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, int, float, cudaStream_t);
+int resample_u8(const uint8_t*, uint8_t*, int64_t, int, int, int, const int*, const int*, int, cudaStream_t);
+int resample_u8_to_chw_bf16(const uint8_t*, void*, int, int, int, int, const int*, const int*, int, float, float, float, cudaStream_t);
 int residual_norm(void*, int64_t, const void*, int64_t, const void*, const void*, void*, int64_t, int, int, float, int, int,
                   cudaStream_t);
 int layernorm(const void*, int64_t, const float*, const float*, void*, int64_t, int, int, float, cudaStream_t);
@@ -74,6 +76,14 @@ int vidi_gemm_bf16_2cta_ln(const void* A, int64_t lda, const void* W, int64_t ld
                            float* stats_out, void* stream) {
     return COUNT(vb::gemm2_bf16_ln(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, res_mod, act, act_param, 0, 0, block_n,
                                    ln_stats, ln_parts, ln_colsum, ln_eps, stats_out, ST(stream)));
+}
+int vidi_resample_u8(const uint8_t* src, uint8_t* dst, int64_t outer, int in_size, int out_size, int inner, const int32_t* xmin,
+                     const int32_t* kk, int ksize, void* stream) {
+    return COUNT(vb::resample_u8(src, dst, outer, in_size, out_size, inner, xmin, kk, ksize, ST(stream)));
+}
+int vidi_resample_u8_to_chw_bf16(const uint8_t* src, void* dst, int F, int in_h, int out_h, int W, const int32_t* ymin,
+                                 const int32_t* kk, int ksize, float rescale, float mean, float stdv, void* stream) {
+    return COUNT(vb::resample_u8_to_chw_bf16(src, dst, F, in_h, out_h, W, ymin, kk, ksize, rescale, mean, stdv, ST(stream)));
 }
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream) {

@@ -428,3 +428,37 @@ for _name in ("rmsnorm", "residual_norm", "layernorm", "mm_finish", "rmsnorm_f32
               "whisper_im2col2", "pool_s2d", "conv_window_gather", "bilinear_ac", "embed_gather", "sinusoid_split", "split3",
               "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text", "text_qk_prep", "xattn_merge2"):
     globals()[_name] = _instrument(globals()[_name])
+
+
+_RESAMPLE_TABLES = {}
+
+
+def _resample_tables(in_size: int, out_size: int, device):
+    """Pillow tap tables (preprocess.pil_bicubic_coeffs) as int32 device tensors, cached per (in, out, device)."""
+    key = (in_size, out_size, str(device))
+    if key not in _RESAMPLE_TABLES:
+        from .preprocess import pil_bicubic_coeffs
+        xmin, kk = pil_bicubic_coeffs(in_size, out_size)
+        _RESAMPLE_TABLES[key] = (xmin.to(device=device, dtype=torch.int32).contiguous(), kk.to(device=device, dtype=torch.int32).contiguous())
+    return _RESAMPLE_TABLES[key]
+
+
+def resize_frames_u8(frames: torch.Tensor, size: int, rescale: float = 1.0 / 255.0, mean: float = 0.5, std: float = 0.5) -> torch.Tensor:
+    """frames uint8 [F,H,W,3] (decoded RGB, on the GPU) -> bf16 [F,3,size,size] = ((PIL_bicubic(frames) * rescale) - mean) / std:
+    process_images' 'resize' branch + SiglipImageProcessor (img_utils.py:181-187), resampling bit-exact with Pillow."""
+    L = _lib.load()
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3 and frames.is_cuda and frames.is_contiguous()
+    F, H, W, _ = frames.shape
+    out = torch.empty(F, 3, size, size, device=frames.device, dtype=BF16)
+    if F == 0:
+        return out
+    mid = frames
+    if W != size:                                   # Pillow skips a pass whose size does not change
+        xmin, kk = _resample_tables(W, size, frames.device)
+        mid = torch.empty(F, H, size, 3, device=frames.device, dtype=torch.uint8)
+        _lib.check(L.vidi_resample_u8(_ptr(frames), _ptr(mid), F * H, W, size, 3, _ptr(xmin), _ptr(kk), kk.shape[1], _stream()),
+                   "resample_u8")
+    ymin, kk = _resample_tables(H, size, frames.device)  # in == out gives the identity taps exactly (weight 1 << 22 on the centre)
+    _lib.check(L.vidi_resample_u8_to_chw_bf16(_ptr(mid), _ptr(out), F, H, size, size, _ptr(ymin), _ptr(kk), kk.shape[1],
+                                              float(rescale), float(mean), float(std), _stream()), "resample_u8_to_chw_bf16")
+    return out
