@@ -105,6 +105,16 @@ int vidi_resample_u8(const uint8_t* src, uint8_t* dst, int64_t outer, int in_siz
 int vidi_resample_u8_to_chw_bf16(const uint8_t* src, void* dst, int F, int in_h, int out_h, int W, const int32_t* ymin,
                                  const int32_t* kk, int ksize, float rescale, float mean, float stdv, void* stream);
 
+/* audio pre-processing: operand builders and finisher of the Whisper log-mel (process_audio, vidi/dataset/vid_utils.py:52-63 -> HF
+ * WhisperFeatureExtractor: hann 400 / hop 160 centred reflect-padded STFT, power, 128 Slaney mel filters, log10 clamp 1e-10, per-chunk
+ * max - 8 floor, (x + 4) / 4, last frame dropped).  The DFT and the mel projection run as vidi_gemm_bf16 in 3-term split-bf16 form:
+ *   vidi_logmel_frames: audio fp32 [C, 480000], window fp32 [400]  -> A1 bf16 [C*3001, 1200] = [hi | hi | lo] of frame * window
+ *   vidi_logmel_power:  Y fp32 [rows, ldy] = [Re 0..200 | Im 0..200 | ...] -> A2 bf16 [rows, 624] = [hi | hi | lo] of |X_k|^2 (padded to 208)
+ *   vidi_logmel_finish: M fp32 [C*3001, mels], chunk_max fp32 [C] (scratch) -> out bf16 [C, mels, 3000] */
+int vidi_logmel_frames(const float* audio, const float* window, void* out, int C, int n_samples, void* stream);
+int vidi_logmel_power(const float* Y, int64_t ldy, void* out, int64_t rows, void* stream);
+int vidi_logmel_finish(const float* M, int C, int mels, float* chunk_max, void* out, void* stream);
+
 /* attention */
 /* bidirectional flash attention for the towers (flash_attn_func via HF SiglipAttention / WhisperAttention), K3/K8 */
 int vidi_attn_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S, int H,

@@ -34,3 +34,26 @@ def test_resize_frames_bit_exact(F, H, W, S):
         assert rc == 0
         from vidi_b200.preprocess import _resample_axis_u8
         assert torch.equal(mid.cpu(), _resample_axis_u8(frames, S, 2))
+
+
+
+@pytest.mark.parametrize("seconds", [7.3, 61.7])
+def test_log_mel_device_matches_torch_restatement(seconds):
+    """ops.log_mel (framing / power / finish kernels around two split-bf16 tensor-core GEMMs) vs WhisperFeatureExtractorLite.log_mel
+    (pinned to the HF extractor at 1e-4 by tests/test_preprocess_cpu.py); tolerance 1e-3 + bf16 output rounding."""
+    import math
+    from vidi_b200 import ops
+    from vidi_b200.preprocess import WhisperFeatureExtractorLite
+    n = int(seconds * 16000)
+    t = torch.arange(n) / 16000.0
+    g = torch.Generator().manual_seed(n)
+    audio = 0.3 * torch.sin(2 * math.pi * 440 * t) * ((t % 3) < 2) + 0.05 * torch.randn(n, generator=g)
+    fe = WhisperFeatureExtractorLite(128)
+    C = -(-n // fe.n_samples)
+    buf = torch.zeros(C * fe.n_samples)
+    buf[:n] = audio
+    ref = fe.log_mel(buf.view(C, -1))
+    out = ops.log_mel(buf.view(C, -1).cuda())
+    assert out.shape == (C, 128, 3000) and out.dtype == torch.bfloat16
+    err = (out.float().cpu() - ref).abs()
+    assert float(err.max()) <= 1e-3 + 2 ** -8 * float(ref.abs().max()), float(err.max())

@@ -16,6 +16,9 @@ int gemm2_bf16(const void*, int64_t, const void*, int64_t, void*, int64_t, int, 
 int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, int, float, cudaStream_t);
 int resample_u8(const uint8_t*, uint8_t*, int64_t, int, int, int, const int*, const int*, int, cudaStream_t);
 int resample_u8_to_chw_bf16(const uint8_t*, void*, int, int, int, int, const int*, const int*, int, float, float, float, cudaStream_t);
+int logmel_frames(const float*, const float*, void*, int, int, cudaStream_t);
+int logmel_power(const float*, int64_t, void*, int64_t, cudaStream_t);
+int logmel_finish(const float*, int, int, float*, void*, cudaStream_t);
 int residual_norm(void*, int64_t, const void*, int64_t, const void*, const void*, void*, int64_t, int, int, float, int, int,
                   cudaStream_t);
 int layernorm(const void*, int64_t, const float*, const float*, void*, int64_t, int, int, float, cudaStream_t);
@@ -84,6 +87,15 @@ int vidi_resample_u8(const uint8_t* src, uint8_t* dst, int64_t outer, int in_siz
 int vidi_resample_u8_to_chw_bf16(const uint8_t* src, void* dst, int F, int in_h, int out_h, int W, const int32_t* ymin,
                                  const int32_t* kk, int ksize, float rescale, float mean, float stdv, void* stream) {
     return COUNT(vb::resample_u8_to_chw_bf16(src, dst, F, in_h, out_h, W, ymin, kk, ksize, rescale, mean, stdv, ST(stream)));
+}
+int vidi_logmel_frames(const float* audio, const float* window, void* out, int C, int n_samples, void* stream) {
+    return COUNT(vb::logmel_frames(audio, window, out, C, n_samples, ST(stream)));
+}
+int vidi_logmel_power(const float* Y, int64_t ldy, void* out, int64_t rows, void* stream) {
+    return COUNT(vb::logmel_power(Y, ldy, out, rows, ST(stream)));
+}
+int vidi_logmel_finish(const float* M, int C, int mels, float* chunk_max, void* out, void* stream) {
+    return COUNT(vb::logmel_finish(M, C, mels, chunk_max, out, ST(stream)));        /* two launches: max, then finish */
 }
 int vidi_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int D, float eps, int add_one,
                  float out_scale, void* stream) {

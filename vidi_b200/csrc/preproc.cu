@@ -57,6 +57,120 @@ __global__ void resample_u8_to_chw_bf16_kernel(const uint8_t* __restrict__ src, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Whisper log-mel on the device (process_audio, vid_utils.py:52-63 -> HF WhisperFeatureExtractor): the 400-point DFT of the 3001
+// hann-windowed, reflect-padded frames of a 30-s chunk and the 201 -> 128 mel projection are two tensor-core GEMMs in the
+// 3-term split-bf16 form already used for the fp32 positional MLPs (x*w ~ xh*wh + xh*wl + xl*wh: A rows hold [hi|hi|lo], W rows
+// [hi|lo|hi]); these kernels only build the operands and finish the features:
+//   logmel_frames:  audio fp32 [C, n]            -> A1 bf16 [C*3001, 3*400]      frame t = samples t*160-200 .. +400 (reflected), * hann
+//   (GEMM 1: A1 x Wdft^T -> Y fp32 [rows, 408] = [Re(0..200) | Im(0..200) | 0])
+//   logmel_power:   Y                             -> A2 bf16 [rows, 3*208]        |X_k|^2, k = 0..200, zero padded
+//   (GEMM 2: A2 x Wmel^T -> M fp32 [rows, 128])
+//   logmel_max:     M -> per-chunk max of log10(max(M, 1e-10)) over the first 3000 frames
+//   logmel_finish:  M -> out bf16 [C, 128, 3000] = (max(log10(...), chunk_max - 8) + 4) / 4     (last frame dropped)
+// ------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_hi_lo(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16(v);
+    lo = __float2bfloat16(v - __bfloat162float(hi));
+}
+
+constexpr int kFft = 400, kHop = 160, kBins = 201, kBinsPad = 208, kFramesPerChunk = 3001;
+
+__global__ void logmel_frames_kernel(const float* __restrict__ audio, const float* __restrict__ window, __nv_bfloat16* __restrict__ out,
+                                     int n_samples) {
+    const int64_t row = blockIdx.x;                                // chunk * 3001 + t
+    const int ch = (int)(row / kFramesPerChunk), t = (int)(row % kFramesPerChunk);
+    const float* a = audio + (int64_t)ch * n_samples;
+    __nv_bfloat16* o = out + row * (3 * kFft);
+    for (int c = threadIdx.x; c < kFft; c += blockDim.x) {
+        int i = t * kHop - kFft / 2 + c;                            // centred frame; torch.stft(center=True, pad_mode="reflect")
+        if (i < 0) i = -i;
+        if (i >= n_samples) i = 2 * (n_samples - 1) - i;
+        __nv_bfloat16 hi, lo;
+        split_hi_lo(a[i] * window[c], hi, lo);
+        o[c] = hi; o[kFft + c] = hi; o[2 * kFft + c] = lo;
+    }
+}
+
+__global__ void logmel_power_kernel(const float* __restrict__ Y, int64_t ldy, __nv_bfloat16* __restrict__ out) {
+    const int64_t row = blockIdx.x;
+    const float* y = Y + row * ldy;
+    __nv_bfloat16* o = out + row * (3 * kBinsPad);
+    for (int k = threadIdx.x; k < kBinsPad; k += blockDim.x) {
+        float p = 0.f;
+        if (k < kBins) { const float re = y[k], im = y[kBins + k]; p = re * re + im * im; }
+        __nv_bfloat16 hi, lo;
+        split_hi_lo(p, hi, lo);
+        o[k] = hi; o[kBinsPad + k] = hi; o[2 * kBinsPad + k] = lo;
+    }
+}
+
+// one block per chunk: max over frames 0..2999 and all mels of log10(max(M, 1e-10))
+__global__ void logmel_max_kernel(const float* __restrict__ M, int mels, float* __restrict__ chunk_max) {
+    const int ch = blockIdx.x;
+    const float* m = M + (int64_t)ch * kFramesPerChunk * mels;
+    float mx = -INFINITY;
+    const int n = (kFramesPerChunk - 1) * mels;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, m[i]);   // log10 is monotone: take it once at the end
+    __shared__ float red[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mx = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (threadIdx.x == 0) chunk_max[ch] = log10f(fmaxf(mx, 1e-10f));
+    }
+}
+
+// M [C*3001, mels] fp32 -> out [C, mels, 3000] bf16; 32 x 32 tiles transposed through shared memory
+__global__ void logmel_finish_kernel(const float* __restrict__ M, int mels, const float* __restrict__ chunk_max,
+                                     __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int ch = blockIdx.z, t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int T = kFramesPerChunk - 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 256 threads: 8 rows per sweep
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, m = m0 + tx;
+        tile[r][tx] = (t < T && m < mels) ? M[((int64_t)ch * kFramesPerChunk + t) * mels + m] : 1.f;
+    }
+    __syncthreads();
+    const float floor_v = chunk_max[ch] - 8.0f;
+    for (int r = ty; r < 32; r += 8) {
+        const int m = m0 + r, t = t0 + tx;
+        if (m < mels && t < T) {
+            const float v = fmaxf(log10f(fmaxf(tile[tx][r], 1e-10f)), floor_v);
+            out[((int64_t)ch * mels + m) * T + t] = __float2bfloat16((v + 4.0f) / 4.0f);
+        }
+    }
+}
+
+int logmel_frames(const float* audio, const float* window, void* out, int C, int n_samples, cudaStream_t st) {
+    VB_REQUIRE(n_samples == (kFramesPerChunk - 1) * kHop, "logmel_frames: chunks must be 30 s at 16 kHz (480000 samples), got %d", n_samples);
+    if (C == 0) return 0;
+    logmel_frames_kernel<<<(unsigned)(C * kFramesPerChunk), 128, 0, st>>>(audio, window, (__nv_bfloat16*)out, n_samples);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int logmel_power(const float* Y, int64_t ldy, void* out, int64_t rows, cudaStream_t st) {
+    VB_REQUIRE(ldy >= 2 * kBins, "logmel_power: ldy %lld < 402", (long long)ldy);
+    if (rows == 0) return 0;
+    logmel_power_kernel<<<(unsigned)rows, 64, 0, st>>>(Y, ldy, (__nv_bfloat16*)out);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+int logmel_finish(const float* M, int C, int mels, float* chunk_max, void* out, cudaStream_t st) {
+    if (C == 0) return 0;
+    logmel_max_kernel<<<C, 1024, 0, st>>>(M, mels, chunk_max);
+    VB_CUDA_CHECK(cudaGetLastError());
+    dim3 grid((kFramesPerChunk - 1 + 31) / 32, (mels + 31) / 32, C);
+    logmel_finish_kernel<<<grid, 256, 0, st>>>(M, mels, chunk_max, (__nv_bfloat16*)out);
+    VB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int resample_u8(const uint8_t* src, uint8_t* dst, int64_t outer, int in_size, int out_size, int inner, const int* xmin,
                 const int* kk, int ksize, cudaStream_t st) {
     VB_REQUIRE(in_size > 0 && out_size > 0 && inner > 0 && ksize > 0, "resample_u8: bad sizes");

@@ -38,6 +38,9 @@ SIGNATURES = {
     "vidi_cast_f32_bf16": [_p, _p, _l, _p],
     "vidi_resample_u8": [_p, _p, _l, _i, _i, _i, _p, _p, _i, _p],
     "vidi_resample_u8_to_chw_bf16": [_p, _p, _i, _i, _i, _i, _p, _p, _i, _f, _f, _f, _p],
+    "vidi_logmel_frames": [_p, _p, _p, _i, _i, _p],
+    "vidi_logmel_power": [_p, _l, _p, _l, _p],
+    "vidi_logmel_finish": [_p, _i, _i, _p, _p, _p],
     "vidi_attn_dense": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_attn_dense_v1": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_attn_dense_v2": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],

@@ -462,3 +462,48 @@ def resize_frames_u8(frames: torch.Tensor, size: int, rescale: float = 1.0 / 255
     _lib.check(L.vidi_resample_u8_to_chw_bf16(_ptr(mid), _ptr(out), F, H, size, size, _ptr(ymin), _ptr(kk), kk.shape[1],
                                               float(rescale), float(mean), float(std), _stream()), "resample_u8_to_chw_bf16")
     return out
+
+
+
+_LOGMEL_TABLES = {}
+
+
+def _logmel_tables(mels: int, device):
+    """hann window, split DFT matrix [408, 1200] (rows: cos 0..200 | -sin 0..200 | 0) and split mel matrix [mels, 624], built in fp64"""
+    key = (mels, str(device))
+    if key not in _LOGMEL_TABLES:
+        import math
+        from .preprocess import mel_filter_bank
+        win = torch.hann_window(400, periodic=True, dtype=torch.float64)
+        ang = torch.arange(201, dtype=torch.float64)[:, None] * torch.arange(400, dtype=torch.float64)[None, :] * (2 * math.pi / 400)
+        dft = torch.zeros(408, 400, dtype=torch.float64)
+        dft[:201], dft[201:402] = torch.cos(ang), -torch.sin(ang)
+        fb = torch.zeros(mels, 208, dtype=torch.float64)
+        fb[:, :201] = mel_filter_bank(201, mels, 16000).t()
+        _LOGMEL_TABLES[key] = (win.float().to(device), split3(dft.float().to(device).contiguous(), 1),
+                               split3(fb.float().to(device).contiguous(), 1))
+    return _LOGMEL_TABLES[key]
+
+
+def log_mel(chunks: torch.Tensor, mels: int = 128, group: int = 16) -> torch.Tensor:
+    """chunks fp32 [C, 480000] (zero-padded 30-s windows of 16 kHz audio, on the GPU) -> bf16 [C, mels, 3000] Whisper log-mel features
+    (WhisperFeatureExtractor semantics, vid_utils.py:52-63); DFT and mel projection on the tensor cores in 3-term split-bf16 form."""
+    L = _lib.load()
+    assert chunks.dtype == torch.float32 and chunks.dim() == 2 and chunks.shape[1] == 480000 and chunks.is_cuda and chunks.is_contiguous()
+    C = chunks.shape[0]
+    out = torch.empty(C, mels, 3000, device=chunks.device, dtype=BF16)
+    if C == 0:
+        return out
+    win, wdft, wmel = _logmel_tables(mels, chunks.device)
+    for c0 in range(0, C, group):                                   # bounds the [rows, 1200] operand (16 chunks = 115 MB)
+        c1 = min(C, c0 + group)
+        rows = (c1 - c0) * 3001
+        a1 = torch.empty(rows, 1200, device=chunks.device, dtype=BF16)
+        _lib.check(L.vidi_logmel_frames(_ptr(chunks[c0:c1]), _ptr(win), _ptr(a1), c1 - c0, 480000, _stream()), "logmel_frames")
+        y = gemm(a1, wdft, out_fp32=True, tag="logmel", alg_k=400)
+        a2 = torch.empty(rows, 624, device=chunks.device, dtype=BF16)
+        _lib.check(L.vidi_logmel_power(_ptr(y), y.stride(0), _ptr(a2), rows, _stream()), "logmel_power")
+        m = gemm(a2, wmel, out_fp32=True, tag="logmel", alg_k=201)
+        cmax = torch.empty(c1 - c0, device=chunks.device, dtype=torch.float32)
+        _lib.check(L.vidi_logmel_finish(_ptr(m), c1 - c0, mels, _ptr(cmax), _ptr(out[c0:c1]), _stream()), "logmel_finish")
+    return out
