@@ -95,3 +95,34 @@ def test_processors_accept_the_reference_call_pattern():
     feats, size = ap(torch.from_numpy(audio))
     assert int(out.num_frames.sum()) == size == len(audio) // 160
     assert out.input_features.shape == (2, 128, 3000) and torch.equal(out.input_features, feats)
+
+
+def test_split_bf16_logmel_arithmetic_is_within_tolerance_of_hf():
+    """Numerics of the device log-mel (csrc/preproc.cu + two 3-term split-bf16 GEMMs), emulated in torch on the CPU: products of
+    bf16 hi/lo pieces (xh*wh + xh*wl + xl*wh) with fp32 accumulation for the 400-point DFT and the mel projection stay within 5e-4 of
+    the HF extractor — far below the bf16 rounding the features get when they enter the model."""
+    import math
+    from transformers import WhisperFeatureExtractor
+    fe = WhisperFeatureExtractor(feature_size=128)
+    n = 16000 * 30
+    t = np.arange(n) / 16000.0
+    rng = np.random.default_rng(1)
+    audio = (0.3 * np.sin(2 * np.pi * 440 * t) * (t % 3 < 2) + 0.05 * rng.standard_normal(n) + 0.2 * np.sin(2 * np.pi * 3000 * t) * (t > 20)).astype(np.float32)
+    ref = fe([audio], sampling_rate=16000, return_tensors="pt")["input_features"][0]
+
+    def split(x):
+        hi = x.to(torch.bfloat16).float()
+        return hi, (x - hi).to(torch.bfloat16).float()
+
+    def mm3(a, w):
+        ah, al = split(a); wh, wl = split(w)
+        return ah @ wh.t() + ah @ wl.t() + al @ wh.t()
+
+    xp = torch.nn.functional.pad(torch.from_numpy(audio)[None, None], (200, 200), mode="reflect")[0, 0]
+    fw = xp.unfold(0, 400, 160) * torch.hann_window(400, periodic=True, dtype=torch.float64).float()
+    ang = torch.arange(201, dtype=torch.float64)[:, None] * torch.arange(400, dtype=torch.float64)[None, :] * (2 * math.pi / 400)
+    re, im = mm3(fw, torch.cos(ang).float()), mm3(fw, (-torch.sin(ang)).float())
+    mel = mm3(re * re + im * im, mel_filter_bank(201, 128, 16000).float().t().contiguous())
+    logs = torch.log10(mel.clamp(min=1e-10))[:-1].t()
+    out = (torch.maximum(logs, logs.max() - 8.0) + 4.0) / 4.0
+    assert float((out - ref).abs().max()) <= 5e-4
