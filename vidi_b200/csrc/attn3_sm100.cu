@@ -83,7 +83,21 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
         : "memory");
 }
 
-template <int DH>
+// 2^x on the FMA pipe (no MUFU): x = n + f with n = rint(x) by the 1.5 * 2^23 trick, a degree-3 polynomial for 2^f on [-0.5, 0.5]
+// (max relative error 7.5e-5, 26x below the bf16 half-ulp of P — tools/exp2_poly.py) and n added to the exponent field.  Used for a
+// share of the scores (kPolyMod below) so that the XU and the issue slots are loaded evenly; NOT ENABLED in the shipped
+// instantiation (kPolyMod = 0) until it has been validated and timed on a B200.
+__device__ __forceinline__ float exp2_poly3(float x) {
+    const float xf = x + 12582912.f;                                   // 1.5 * 2^23: low mantissa bits now hold rint(x)
+    const float f = x - (xf - 12582912.f);
+    float q = fmaf(0.0551716387f, f, 0.242611125f);
+    q = fmaf(q, f, 0.693260968f);
+    q = fmaf(q, f, 0.999928057f);
+    const int bits = __float_as_int(q) + (__float_as_int(xf) << 23);  // (n + 0x4B400000) << 23 == n << 23 mod 2^32
+    return x < -126.f ? 0.f : __int_as_float(bits);                    // ragged / far-below-reference keys -> exactly 0
+}
+
+template <int DH, int kPolyMod>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd3_sm100_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __grid_constant__ CUtensorMap tm_q_tail,
                        const __grid_constant__ CUtensorMap tm_k_main, const __grid_constant__ CUtensorMap tm_k_tail,
@@ -309,8 +323,13 @@ attn_fwd3_sm100_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gr
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float e0, e1;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_ref)));
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_ref)));
+                            if (kPolyMod > 0 && (i % (kPolyMod > 0 ? kPolyMod : 1)) == 0) {     // this pair of scores goes to the FMA pipe
+                                e0 = exp2_poly3(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_ref));
+                                e1 = exp2_poly3(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_ref));
+                            } else {
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_ref)));
+                                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_ref)));
+                            }
                             pk[cc * 16 + i] = pack_bf16(e0, e1);
                             ored |= pk[cc * 16 + i];
                         }
@@ -417,7 +436,7 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     }
     static bool attr = false;
     if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_sm100_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_sm100_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr = true;
     }
     Fa3Params p;
@@ -429,7 +448,7 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
     const int grid = p.items < num_sms() ? p.items : num_sms();
-    attn_fwd3_sm100_kernel<DH><<<grid, 384, C::kSmem, st>>>(tm_q_main, tm_q_tail, tm_k_main, tm_k_tail, p);
+    attn_fwd3_sm100_kernel<DH, 0><<<grid, 384, C::kSmem, st>>>(tm_q_main, tm_q_tail, tm_k_main, tm_k_tail, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
