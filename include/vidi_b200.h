@@ -126,6 +126,10 @@ int vidi_attn_dense_v1(const void* qkv, int64_t ld, int q_off, int k_off, int v_
  * (P and O resident in tensor memory) */
 int vidi_attn_dense_v2(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                        int H, int dh, float scale, void* stream);
+/* A/B entry, not on the product path and not yet validated on a GPU: the current kernel with every poly_mod-th (2, 3 or 4) pair of scores
+ * exponentiated by an FMA-pipe polynomial instead of MUFU.EX2 (packed qkv [B*S, 3*H*dh], dh 64 / 72, S > 128) */
+int vidi_attn_dense_poly(const void* qkv, int64_t ld, void* out, int64_t ldo, int B, int S, int H, int dh, float scale, int poly_mod,
+                         void* stream);
 /* same contract, always the warp-level mma.sync kernel (generic strides / head dims; kept as the A/B bar for the tcgen05 path) */
 int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                         int H, int dh, float scale, void* stream);

@@ -57,3 +57,18 @@ def test_log_mel_device_matches_torch_restatement(seconds):
     assert out.shape == (C, 128, 3000) and out.dtype == torch.bfloat16
     err = (out.float().cpu() - ref).abs()
     assert float(err.max()) <= 1e-3 + 2 ** -8 * float(ref.abs().max()), float(err.max())
+
+
+@pytest.mark.parametrize("poly", [2, 3, 4])
+@pytest.mark.parametrize("B,S,H,dh", [(3, 729, 4, 72), (2, 1500, 4, 64), (2, 300, 2, 64)])
+def test_attn_dense_poly_exp2_variants(B, S, H, dh, poly):
+    """parked A/B variants of the tower attention with an FMA-pipe exp2 polynomial on every poly-th score pair (ops.attn_dense impl="polyN")"""
+    from vidi_b200 import ops
+    d = H * dh
+    g = torch.Generator(device="cuda").manual_seed(S + poly)
+    qkv = torch.randn(B * S, 3 * d, device="cuda", generator=g).to(torch.bfloat16)
+    out = ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, impl=f"poly{poly}")
+    q, k, v = [t.float().view(B, S, H, dh).transpose(1, 2) for t in qkv.split(d, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1) @ v).transpose(1, 2).reshape(B * S, d)
+    err = float((out.float() - ref).norm() / ref.norm())
+    assert err < 8e-3, err

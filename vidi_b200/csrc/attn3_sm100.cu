@@ -416,7 +416,7 @@ attn_fwd3_sm100_kernel(const __grid_constant__ CUtensorMap tm_q_main, const __gr
     }
 }
 
-template <int DH>
+template <int DH, int kPolyMod>
 static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B, int S, int H, float scale, cudaStream_t st) {
     using C = Fa3Cfg<DH>;
     CUtensorMap tm_q_main, tm_q_tail, tm_k_main, tm_k_tail;
@@ -436,7 +436,7 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     }
     static bool attr = false;
     if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_sm100_kernel<DH, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_sm100_kernel<DH, kPolyMod>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr = true;
     }
     Fa3Params p;
@@ -448,7 +448,7 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
     const int grid = p.items < num_sms() ? p.items : num_sms();
-    attn_fwd3_sm100_kernel<DH, 0><<<grid, 384, C::kSmem, st>>>(tm_q_main, tm_q_tail, tm_k_main, tm_k_tail, p);
+    attn_fwd3_sm100_kernel<DH, kPolyMod><<<grid, 384, C::kSmem, st>>>(tm_q_main, tm_q_tail, tm_k_main, tm_k_tail, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -458,9 +458,25 @@ int attn_dense_sm100_v3(const void* qkv, int64_t ld, void* out, int64_t ldo, int
     VB_REQUIRE(ld == (int64_t)3 * H * dh, "attn_dense_sm100_v3: qkv must be packed [B*S, 3*H*dh]");
     VB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ldo % 8 == 0, "attn_dense_sm100_v3: alignment");
     if (B == 0 || S == 0) return 0;
-    if (dh == 72) return launch_fa3<72>(qkv, ld, out, ldo, B, S, H, scale, st);
-    if (dh == 64) return launch_fa3<64>(qkv, ld, out, ldo, B, S, H, scale, st);
+    if (dh == 72) return launch_fa3<72, 0>(qkv, ld, out, ldo, B, S, H, scale, st);
+    if (dh == 64) return launch_fa3<64, 0>(qkv, ld, out, ldo, B, S, H, scale, st);
     VB_REQUIRE(false, "attn_dense_sm100_v3: unsupported head_dim %d", dh);
+}
+
+// A/B entry for the FMA-pipe exp2 share (kPolyMod = 2, 3 or 4: every kPolyMod-th pair of scores bypasses MUFU).  Not used by
+// vidi_attn_dense; exists so that the option can be validated and timed (tests/test_preprocess_gpu.py is not the place: see
+// tests/test_kernels_gpu.py::test_attn_dense_poly, parked with the other not-yet-run GPU tests).
+int attn_dense_sm100_v3_poly(const void* qkv, int64_t ld, void* out, int64_t ldo, int B, int S, int H, int dh, float scale,
+                             int poly_mod, cudaStream_t st) {
+    VB_REQUIRE(ld == (int64_t)3 * H * dh, "attn_dense_sm100_v3_poly: qkv must be packed [B*S, 3*H*dh]");
+    VB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && ldo % 8 == 0, "attn_dense_sm100_v3_poly: alignment");
+    VB_REQUIRE(S > 128, "attn_dense_sm100_v3_poly: S must exceed 128 (needs >= 3 key tiles)");
+    if (B == 0) return 0;
+#define VB_POLY_CASE(D, P) if (dh == D && poly_mod == P) return launch_fa3<D, P>(qkv, ld, out, ldo, B, S, H, scale, st)
+    VB_POLY_CASE(72, 2); VB_POLY_CASE(72, 3); VB_POLY_CASE(72, 4);
+    VB_POLY_CASE(64, 2); VB_POLY_CASE(64, 3); VB_POLY_CASE(64, 4);
+#undef VB_POLY_CASE
+    VB_REQUIRE(false, "attn_dense_sm100_v3_poly: unsupported head_dim %d / poly_mod %d", dh, poly_mod);
 }
 
 }  // namespace vb

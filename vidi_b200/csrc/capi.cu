@@ -39,6 +39,7 @@ int attn_dense(const void*, int64_t, int, int, int, void*, int64_t, int, int, in
 int attn_dense_sm100(const void*, int64_t, void*, int64_t, int, int, int, int, float, cudaStream_t);
 int attn_dense_sm100_pp(const void*, int64_t, void*, int64_t, int, int, int, int, float, cudaStream_t);
 int attn_dense_sm100_v3(const void*, int64_t, void*, int64_t, int, int, int, int, float, cudaStream_t);
+int attn_dense_sm100_v3_poly(const void*, int64_t, void*, int64_t, int, int, int, int, float, int, cudaStream_t);
 int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int, float,
                   float, float*, float*, int, cudaStream_t);
 int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int, float, int, float*, cudaStream_t);
@@ -167,6 +168,10 @@ int vidi_attn_dense_v2(const void* qkv, int64_t ld, int q_off, int k_off, int v_
     if ((dh == 72 || dh == 64) && q_off == 0 && k_off == H * dh && v_off == 2 * H * dh && ld == (int64_t)3 * H * dh)
         return COUNT(vb::attn_dense_sm100_pp(qkv, ld, out, ldo, B, S, H, dh, scale, ST(stream)));
     return COUNT(vb::attn_dense(qkv, ld, q_off, k_off, v_off, out, ldo, B, S, H, dh, scale, ST(stream)));
+}
+int vidi_attn_dense_poly(const void* qkv, int64_t ld, void* out, int64_t ldo, int B, int S, int H, int dh, float scale, int poly_mod,
+                         void* stream) {
+    return COUNT(vb::attn_dense_sm100_v3_poly(qkv, ld, out, ldo, B, S, H, dh, scale, poly_mod, ST(stream)));
 }
 int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                         int H, int dh, float scale, void* stream) {

@@ -44,6 +44,7 @@ SIGNATURES = {
     "vidi_attn_dense": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_attn_dense_v1": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_attn_dense_v2": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
+    "vidi_attn_dense_poly": [_p, _l, _p, _l, _i, _i, _i, _i, _f, _i, _p],
     "vidi_attn_dense_mma": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_xattn_splitkv": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_splitkv_mma": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],

@@ -302,6 +302,10 @@ def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None, imp
     assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
     if out is None:
         out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
+    if impl.startswith("poly"):          # A/B only: FMA-pipe exp2 for every (2|3|4)-th score pair, e.g. impl="poly4"
+        _lib.check(L.vidi_attn_dense_poly(_ptr(qkv), _rowmajor(qkv), _ptr(out), _rowmajor(out), B, S, H, dh, scale, int(impl[4:]),
+                                          _stream()), "attn_dense_poly")
+        return out
     fn = L.vidi_attn_dense_mma if impl == "mma" else L.vidi_attn_dense_v1 if impl == "v1" else L.vidi_attn_dense_v2 if impl == "v2" else L.vidi_attn_dense
     _lib.check(fn(_ptr(qkv), _rowmajor(qkv), 0, d, 2 * d, _ptr(out), _rowmajor(out), B, S, H, dh, scale, _stream()),
                "attn_dense")
