@@ -1,6 +1,7 @@
 """Micro-benchmarks of the hot kernels (CUDA events, L2-flushed between iterations) next to the library bar
 (torch.matmul -> cuBLAS, flash-attn 2) the reference would run on the same B200.  Not the headline bench."""
 import json
+import os
 import sys
 import time
 
@@ -68,6 +69,10 @@ def dense_case(B, S, H, dh):
     t_2 = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="v2"))
     rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), v1_tflops=round(fl / t_1 / 1e9, 1), v2_tflops=round(fl / t_2 / 1e9, 1), mma_ms=round(t_m, 4),
                mma_tflops=round(fl / t_m / 1e9, 1))
+    if os.environ.get("VIDI_RUN_UNVALIDATED") == "1":          # parked A/B variants: FMA-pipe exp2 on every N-th score pair
+        for n in (2, 3, 4):
+            t_p = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl=f"poly{n}"))
+            rec[f"poly{n}_tflops"] = round(fl / t_p / 1e9, 1)
     try:
         from flash_attn import flash_attn_func
         q, k, v = [x.reshape(B, S, H, dh) for x in qkv.split(d, 1)]
