@@ -165,3 +165,23 @@ def test_bench_reference_arm_prints_contract_line():
     out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """include/vidi_b200.h is a C header (no C++ / torch types): a strict-C99 translation unit includes it, links the in-tree shared
+    library and calls an entry point that needs no GPU."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "vidi_b200")
+    exe = str(tmp_path / "abi_smoke")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                         os.path.join(root, "tests", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lvidi_b200", f"-Wl,-rpath,{libdir}",
+                         "-Wl,--allow-shlib-undefined"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.startswith("abi="), (run.stdout, run.stderr)
