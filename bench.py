@@ -52,6 +52,56 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src="fallback")
 
 
+MEASURED_TRAFFIC_SRC = "profiles/ncu_traffic.json"
+
+
+def measured_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this round (None if absent)"""
+    p = os.path.join(ROOT, MEASURED_TRAFFIC_SRC)
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get(key, {}).get("dram_bytes")
+
+
+def multi_gpu_parity_check(eng, cfg, rank, world, dev):
+    """N-rank prefill vs the same engine as ONE rank (rank 0), on a small synthetic video, before timing.  Replaces the reference's
+    Gather.forward (all_to_all.py:361): wrong rank strides / flags / shard offsets would show up here, not in a fast wrong number."""
+    import copy
+    import torch.distributed as dist
+    from vidi_b200.engine import make_plan
+    F, Cn = 2 * world + 3, world - 1 if world > 2 else 2
+    asz = Cn * 3000 - 1300
+    g = torch.Generator(device=dev); g.manual_seed(99)
+    images = torch.randn(F, 3, 384, 384, generator=g, device=dev).clamp_(-1, 1).to(torch.bfloat16)
+    mels = (0.5 * torch.randn(Cn, 128, 3000, generator=g, device=dev)).to(torch.bfloat16)
+    ids = torch.randint(3, cfg.llm.vocab, (24,), generator=g, device=dev)
+    plan = make_plan(cfg, F, Cn, asz, rank, world)
+    logits = eng.prefill(ids, images[plan.f0:plan.f1], mels[plan.c0:plan.c1], asz, n_frames_total=F, n_chunks_total=Cn)
+    ref0 = logits.clone()
+    dist.broadcast(ref0, 0)
+    same = torch.tensor([1 if torch.equal(ref0, logits) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    res = torch.zeros(3, device=dev)
+    if rank == 0:
+        one = copy.copy(eng)
+        one.rank, one.world, one.xchg = 0, 1, None
+        full = one.prefill(ids, images, mels, asz)
+        err = float((logits - full).abs().max())
+        top2 = full.topk(2, -1).values
+        dec = (top2[:, 0] - top2[:, 1]) > 4 * err
+        res = torch.tensor([float((logits - full).norm() / full.norm()), err,
+                            1.0 if torch.equal(logits.argmax(-1)[dec], full.argmax(-1)[dec]) else 0.0], device=dev)
+    dist.broadcast(res, 0)
+    out = dict(workload=f"{F} frames / {Cn} chunks / 24 text tokens at full 9B dims, world {world} vs world 1 on rank 0",
+               rel_l2=round(float(res[0]), 6), max_abs=round(float(res[1]), 5), argmax_equal_on_decisive=bool(res[2] == 1.0),
+               ranks_bit_equal=bool(same.item()), tolerance="rel_l2 <= 1e-2")
+    if not (out["rel_l2"] <= 1e-2 and out["argmax_equal_on_decisive"] and out["ranks_bit_equal"]):
+        raise RuntimeError(f"multi-GPU parity check failed, refusing to time a wrong path: {out}")
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons of one GPU during the timed region (pynvml)."""
 
@@ -236,14 +286,18 @@ def run_ours(args):
     plan = make_plan(cfg, F, Cn, asz, rank, world)
     ids = torch.randint(3, cfg.llm.vocab, (1, T + 1), generator=g); ids[0, 0] = 2; ids[0, 1] = -200
     g_dev = torch.Generator(device=dev); g_dev.manual_seed(4321)
-    # each rank pins only its contiguous shard of frames / chunks on the host (mm_total mode of the facade)
+    # each rank pins only its contiguous shard of frames / chunks on the host (mm_total mode of the facade).  Frames are generated in
+    # GLOBAL blocks of 64 (seed = 4321 + block index), so the video is the same at every N and the logits digest below is comparable
+    # across the 1/2/4/8-GPU lines.
     fl = plan.f1 - plan.f0
     host_img = torch.empty(1, fl, 3, 384, 384, dtype=torch.bfloat16).pin_memory()
-    chunk = 256
-    for s in range(0, fl, chunk):
-        e = min(fl, s + chunk)
-        gi = torch.Generator(device=dev); gi.manual_seed(4321 + plan.f0 + s)
-        host_img[0, s:e].copy_(torch.randn(e - s, 3, 384, 384, generator=gi, device=dev).clamp_(-1, 1).to(torch.bfloat16))
+    blk = 64
+    for b in range(plan.f0 // blk, -(-plan.f1 // blk) if fl else 0):
+        gi = torch.Generator(device=dev); gi.manual_seed(4321 + b)
+        frames = torch.randn(blk, 3, 384, 384, generator=gi, device=dev).clamp_(-1, 1).to(torch.bfloat16)
+        lo, hi = max(plan.f0, b * blk), min(plan.f1, (b + 1) * blk)
+        host_img[0, lo - plan.f0:hi - plan.f0].copy_(frames[lo - b * blk:hi - b * blk])
+        del frames
     host_mel = (0.5 * torch.randn(1, Cn, 128, 3000, generator=g))[:, plan.c0:plan.c1].to(torch.bfloat16).contiguous().pin_memory()
     dev_img = host_img[0].to(dev)
     dev_mel = host_mel[0].to(dev)
@@ -290,6 +344,11 @@ def run_ours(args):
             ms = float(t)
         return ms, launches, prof
 
+    # Multi-GPU pre-flight (before anything is timed): the N-rank path must reproduce the SAME engine run as one rank.  A small video
+    # (uneven frame split, ranks without audio) is prefetched at world N by all ranks and at world 1 by rank 0; a mismatch aborts.
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity_check(eng, cfg, rank, world, dev)
     for _ in range(1 if args.quick else max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -325,9 +384,10 @@ def run_ours(args):
         top_launch = dict(kernel="gemm_bf16_kernel<256> GeGLU epilogue", shape=[M_loc, 2 * cfg.llm.inter, cfg.llm.hidden], bound="tensor",
                           achieved=round(fl / avg_ms / 1e9, 1), peak=pk["tensor"], unit="TFLOP/s", frac=round(fl / avg_ms / 1e9 / pk["tensor"], 4),
                           ms_per_launch=round(avg_ms, 3), launches_per_step=gu[2] // args.steps,
-                          # ncu dram__bytes (M=126000): 13.65+3.61 GB before the L2-sized tile groups (r01_ncu_full_summary_v2.txt), 7.74+3.60 GB after
-                          # (profiles/r01_ncu_gateup126k_traffic_after_l2_groups.txt)
-                          traffic=11340000000 if (world == 1 and args.workload == "c3") else None,
+                          # dram__bytes of this launch from the round's committed ncu capture (profiles/ncu_traffic.json, written by
+                          # tools/ncu_traffic.py from an `ncu --set full` run of tools/bench_kernels.py); never a typed-in constant
+                          traffic=measured_traffic("gate_up126k") if (world == 1 and args.workload == "c3") else None,
+                          traffic_src=MEASURED_TRAFFIC_SRC,
                           algorithmic_bytes=int(M_loc * cfg.llm.hidden * 2 + 2 * cfg.llm.inter * cfg.llm.hidden * 2 + M_loc * cfg.llm.inter * 2))
     # replicated text pass alone (the Amdahl term of the multi-GPU run): CUDA events around engine.text_pass on a prebuilt cache
     text_ms = None
@@ -350,6 +410,14 @@ def run_ours(args):
         for _ in range(2):
             step_e2e()
         ms_e2e, _, _ = timed(step_e2e, args.steps)
+    # digest of the last timed step's logits (same video at every N -> comparable across the scaling lines)
+    last = step_device().float()
+    torch.cuda.synchronize()
+    top = last[-1].topk(5)
+    digest = dict(argmax_last=int(top.indices[0]), top5_last=[int(i) for i in top.indices], top5_logits=[round(float(v), 3) for v in top.values],
+                  l2=round(float(last.norm()), 3), mean_abs=round(float(last.abs().mean()), 5),
+                  argmax_all_positions_crc=int(last.argmax(-1).to(torch.int64).mul(torch.arange(1, last.shape[0] + 1, device=last.device)).sum() % 1000003))
+    del last
     h2d = (dev_img.numel() * 2 + dev_mel.numel() * 2 + ids.numel() * 8) * clips
     d2h = cfg.llm.vocab * 4 * clips
     if rank != 0:
@@ -370,10 +438,12 @@ def run_ours(args):
                             l2="inputs and activations >> 126 MB L2; no explicit flush"),
                 roofline=roofline, roofline_top_launch=top_launch, cpu_baseline=cpu,
                 e2e=dict(value=round(e2e_v, 1), unit=UNIT, ms_per_step=round(ms_e2e / args.steps, 2), h2d_bytes_per_step=h2d,
-                         d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors"),
+                         d2h_bytes_per_step=d2h, api="DattnGemma2ForCausalLM.forward(input_ids, images=, audios=, audio_sizes=) with pinned host tensors",
+                         note="host tensors are bf16 (the reference's ask() casts to half on the host before .cuda(), inference.py:23,27: that cast is "
+                              "outside this region too); mm_total=(F, C) tells the facade that each rank was handed only its own shard of frames / chunks"),
                 other_ops_ms_per_step={k: v[0] for k, v in sorted(getattr(timed, "by_op", {}).items(), key=lambda kv: -kv[1][0])},
                 gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
-                text_pass_ms=text_ms,
+                text_pass_ms=text_ms, logits_digest=digest, multi_gpu_parity=parity, exchange=eng.exchange_note,
                 gemm_variant="2cta (cta_group::2) on tower/projector sites with M>=1024, 1cta on stream-pass and text sites" if ops.USE_2CTA else "1cta")
     print(json.dumps(line), flush=True)
 

@@ -156,6 +156,26 @@ int vidi_text_qk_prep(const void* qkv, int64_t ld, void* q_rope, int64_t ldq, vo
 int vidi_xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0, const float* O1,
                       const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
                       int rows, int dh, void* out_bf16, void* stream);
+/* Multi-GPU exchange of the text stream's cross-attention partials over NVLink peer memory; replaces the reference's
+ * sequence-parallel Gather.forward / all-gather (lmm/dattn/sequence_parallel/all_to_all.py:361, split.py:72-93).
+ *  vidi_xattn_premerge_push: LSE-merge this rank's P0 (P1) key splits of stream 0 (1) into one (O [rows,dh], LSE [rows]) partial per
+ *      stream and store it at float offset my_block_off of every peer_base[r] (r < world; peer-mapped device pointers, layout per
+ *      stream: O | LSE); when peer_flag is non-NULL the last block publishes `seq` in *peer_flag[r] of every rank (release, system
+ *      scope).  counter: one zero-initialised uint32 of scratch on this device.
+ *  vidi_xattn_merge2_sync: vidi_xattn_merge2 that first waits until flags[0..nflags) (this rank's own flag words, one per source
+ *      rank) have all reached `seq`; *err is set to 1 if a peer never arrives (bounded spin, ~3 s).
+ *  vidi_p2p_*: the exchange arena itself -- cudaMalloc + CUDA IPC export / import (one process per GPU, same node). */
+int vidi_xattn_premerge_push(const float* O0, const float* L0, int P0, const float* O1, const float* L1, int P1, int nsrc, int rows,
+                             int dh, float* const* peer_base, uint32_t* const* peer_flag, int world, int64_t my_block_off,
+                             uint32_t seq, uint32_t* counter, void* stream);
+int vidi_xattn_merge2_sync(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0,
+                           const float* O1, const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc,
+                           const float* att, int rows, int dh, void* out_bf16, const uint32_t* flags, int nflags, uint32_t seq,
+                           int* err, void* stream);
+int vidi_p2p_alloc(int64_t bytes, void** ptr, void* ipc_handle_64_bytes);
+int vidi_p2p_open(const void* ipc_handle_64_bytes, void** ptr);
+int vidi_p2p_close(void* ptr);
+int vidi_p2p_free(void* ptr);
 int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream);
 /* causal text self attention with soft-cap and sliding window (HF Gemma2Attention via gemma.py:165-175), K16 */
 int vidi_attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int Tq, int Tk, int pos0, int Hq,

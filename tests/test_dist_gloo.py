@@ -1,6 +1,9 @@
-"""world_size=2 gloo test of the multi-rank host logic: shard plan + the flat [O | LSE] all-gather layout + the
-rank-strided log-sum-exp merge indexing that engine.text_pass hands to vidi_xattn_merge.  The per-rank partials are
-produced by the oracle's attention on CPU (the CUDA kernel's own parity is covered by the -m gpu tests)."""
+"""world_size=2 gloo test of the multi-rank host logic: shard plan + the per-rank pre-merge of the key splits (xchg.cu
+xattn_premerge_push) + the exchange of the reduced [O | LSE] blocks + the rank-strided log-sum-exp merge indexing that
+engine._TextRun hands to vidi_xattn_merge2 (spr = 1, rank stride = block).  The per-rank partials are produced by the oracle's
+attention on CPU; the CUDA kernels' own parity, and the engine's multi-rank branches, are covered by the -m gpu tests
+(test_kernels_gpu.py::test_premerge_then_rank_strided_merge2, test_engine_gpu.py::test_multirank_text_path_lockstep_equals_single_rank,
+test_dist_nccl_gpu.py)."""
 import os
 
 import torch
@@ -18,6 +21,16 @@ def merge_like_kernel(gathered, P, spr, rank_stride, o_off, l_off, rows, dh):
         base = (p // spr) * rank_stride + o_off + (p % spr) * rows * dh
         out += w[p][:, None] * gathered[base:base + rows * dh].view(rows, dh)
     return out / w.sum(0)[:, None]
+
+
+def premerge_like_kernel(O, Ls):
+    """Python mirror of xattn_premerge_push_kernel: [P, rows, dh], [P, rows] -> flat [O rows*dh | LSE rows]"""
+    Lm = Ls.max(0).values
+    w = torch.where(torch.isinf(Ls), torch.zeros_like(Ls), torch.exp(Ls - torch.where(torch.isinf(Lm), torch.zeros_like(Lm), Lm)))
+    den = w.sum(0)
+    o = (w[:, :, None] * O).sum(0) * torch.where(den > 0, 1.0 / den, torch.zeros_like(den))[:, None]
+    lse = torch.where(den > 0, Lm + torch.log(den), torch.full_like(den, float("-inf")))
+    return torch.cat([o.reshape(-1), lse])
 
 
 def worker(rank, world, port, ret):
@@ -54,12 +67,12 @@ def worker(rank, world, port, ret):
 
     Oi, Li = partials(K_img, V_img, plan.f0 * plan.tpf, plan.f1 * plan.tpf)
     Oa, La = partials(K_aud, V_aud, plan.a0, plan.a1)
-    flat = torch.cat([Oi.reshape(-1), Li.reshape(-1), Oa.reshape(-1), La.reshape(-1)])
+    flat = torch.cat([premerge_like_kernel(Oi, Li), premerge_like_kernel(Oa, La)])     # one reduced block per rank
     gathered = torch.empty(world * flat.numel())
     dist.all_gather_into_tensor(gathered, flat)
-    sz = spr * rows * (dh + 1)
-    out_i = merge_like_kernel(gathered, world * spr, spr, flat.numel(), 0, spr * rows * dh, rows, dh)
-    out_a = merge_like_kernel(gathered, world * spr, spr, flat.numel(), sz, sz + spr * rows * dh, rows, dh)
+    sz = rows * (dh + 1)
+    out_i = merge_like_kernel(gathered, world, 1, flat.numel(), 0, rows * dh, rows, dh)
+    out_a = merge_like_kernel(gathered, world, 1, flat.numel(), sz, sz + rows * dh, rows, dh)
 
     def full(K, V):
         k = K.repeat_interleave(c.groups, 0); v = V.repeat_interleave(c.groups, 0)

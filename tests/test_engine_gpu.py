@@ -137,6 +137,64 @@ def test_sharded_equals_single_rank_fake_multirank():
     assert rel(logits2, full) < 1e-2
 
 
+def _lockstep_world(eng, cfg, world, ids_dev, images, mels, asz, F, Cn, family_mistral=False):
+    """Run the REAL multi-rank text path for `world` fake ranks on one device: each fake rank is a shallow copy of the engine (shared
+    weights) with its own rank / world / peer-exchange handle; encode + stream pass per rank, then all ranks' _TextRun objects advance
+    layer by layer in lock step (begin: partials + push; end: flag wait + rank merge).  Exercises engine.py's `world > 1` branches,
+    splits sized from ceil(n_total / world), premerge + peer stores + rank-strided merge -- everything but the IPC mapping."""
+    import copy
+    from vidi_b200.engine import _TextRun, make_plan
+    from vidi_b200.exchange import PartialExchange
+    c = cfg.llm
+    xs = PartialExchange.local_group(world, PartialExchange.capacity(ids_dev.numel() * c.heads, c.head_dim))
+    runs, plans = [], []
+    for r in range(world):
+        e = copy.copy(eng)
+        e.rank, e.world, e.xchg = r, world, xs[r]
+        plan = make_plan(cfg, F, Cn, asz, r, world)
+        S, seg = e.encode_streams(images[plan.f0:plan.f1], mels[plan.c0:plan.c1], plan)
+        kv = e.stream_pass(S)
+        run = _TextRun(e, ids_dev, kv, seg, None, 0)
+        assert run.mode == "p2p"
+        runs.append(run); plans.append(plan)
+    for l in range(c.layers):
+        for run in runs:
+            run.layer_begin(l)
+        for run in runs:
+            run.layer_end(l)
+    outs = [run.finish() for run in runs]
+    torch.cuda.synchronize()
+    for x in xs:
+        x.check()
+    return outs, plans
+
+
+@pytest.mark.parametrize("world,F,Cn,asz", [(2, 5, 3, 7000), (3, 5, 2, 4100), (8, 9, 3, 8200)])
+def test_multirank_text_path_lockstep_equals_single_rank(world, F, Cn, asz):
+    """N-rank vs 1-rank logits through the engine's own multi-rank code (replacement of Gather.forward, all_to_all.py:361):
+    uneven frame split, ranks with zero audio chunks (world 3: 2 chunks; world 8: 3 chunks), a partial last audio chunk."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_mini
+    cfg = vidi15_mini()
+    sd, eng = build(cfg)
+    ids, images, mels, asz = synth.make_inputs(cfg, F, Cn, n_text=11, audio_size=asz)
+    images = images.cuda().to(BF); mels = mels.cuda().to(BF)
+    ids_dev = R.strip_image_token(ids).cuda()
+    full = eng.prefill(ids_dev, images, mels, asz)
+    outs, plans = _lockstep_world(eng, cfg, world, ids_dev, images, mels, asz, F, Cn)
+    assert any(p.n_aud == 0 for p in plans) or world == 2
+    assert sum(p.n_img for p in plans) == plans[0].n_img_total and sum(p.n_aud for p in plans) == plans[0].n_aud_total
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])               # every rank merges the same partials in the same order
+    assert rel(outs[0], full) < 1e-2, rel(outs[0], full)
+    ref = R.prefill(sd, cfg, ids, images.float().cpu(), mels.float().cpu(), asz, normalizer_dtype=BF)
+    err = float((outs[0].cpu() - ref).abs().max())
+    assert rel(outs[0], ref) < 3e-2 and err < 0.25
+    top2 = ref.topk(2, -1).values
+    confident = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert torch.equal(outs[0].cpu().argmax(-1)[confident], ref.argmax(-1)[confident])
+
+
 def test_vidi7b_prefill_mini():
     """Vidi-7B (Mistral Dattn): learned-conv pooling, SwiGLU, no post-norms / soft-caps, dh=128."""
     from oracle import synth, vidi7b_ref as R7

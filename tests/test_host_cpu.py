@@ -20,7 +20,7 @@ def test_library_exports_every_header_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/vidi_b200.h but not exported"
     assert declared == set(lib.SIGNATURES) | set(lib.EXTRA_SYMBOLS)
-    assert L.vidi_abi_version() == 1
+    assert L.vidi_abi_version() == 2
     assert isinstance(L.vidi_launch_count(), int)
 
 

@@ -406,3 +406,111 @@ def test_text_qk_prep_and_merge2_match_unfused_path():
     out1 = torch.empty(rows, dh, device="cuda", dtype=BF)
     ops.xattn_merge2([], att, out1, rows, dh)
     assert torch.equal(out1, att.to(BF))
+
+
+def _merge_ref(parts):
+    """fp64 reference: merge a list of (O [rows, dh], LSE [rows]) partials -> (O, LSE)"""
+    lse = torch.stack([l for _, l in parts]).double()
+    Lm = lse.max(0).values
+    Lm = torch.where(torch.isinf(Lm), torch.zeros_like(Lm), Lm)
+    w = torch.exp(lse - Lm)
+    den = w.sum(0)
+    O = sum(w[i][:, None] * parts[i][0].double() for i in range(len(parts))) / den.clamp_min(1e-300)[:, None]
+    O = torch.where(den[:, None] > 0, O, torch.zeros_like(O))
+    return O, torch.where(den > 0, Lm + torch.log(den), torch.full_like(den, float("-inf")))
+
+
+@pytest.mark.parametrize("world,dh", [(2, 256), (3, 128), (8, 256)])
+def test_premerge_then_rank_strided_merge2(world, dh):
+    """The multi-rank receive path at kernel level: every fake rank reduces its own key splits with xattn_premerge into its block of
+    a gathered buffer (the layout one all-gather of the reduced blocks produces), then xattn_merge2 reads the blocks in place with a
+    NON-ZERO rank stride.  One rank holds no valid key for stream 1 (all LSE = -inf); one stream has a zero gate."""
+    from vidi_b200 import ops
+    rows = 7 * 4
+    splits = [(5, 3), (4, 2), (6, 1), (2, 2), (1, 1), (3, 3), (2, 1), (4, 4)][:world]
+    block = 2 * rows * (dh + 1)
+    gathered = torch.full((world * block + 64,), float("nan"), device="cuda")
+    per_stream = [[], []]
+    for r, sp in enumerate(splits):
+        srcs = []
+        for si, P in enumerate(sp):
+            O = rnd(P, rows, dh, seed=100 + 10 * r + si).float().contiguous()
+            Ls = (3.0 * rnd(P, rows, seed=200 + 10 * r + si)).float().contiguous()
+            Ls[0, ::5] = float("-inf")
+            if r == 1 and si == 1:
+                Ls[:] = float("-inf")
+            srcs.append((O, Ls, P))
+            per_stream[si].append(_merge_ref([(O[p].cpu(), Ls[p].cpu()) for p in range(P)]))
+        pre = gathered[r * block:(r + 1) * block]
+        ops.xattn_premerge(srcs, rows, dh, pre)
+        for si in range(2):                      # the reduced partial itself
+            o = pre[si * rows * (dh + 1):][:rows * dh].view(rows, dh).cpu().double()
+            l = pre[si * rows * (dh + 1) + rows * dh:][:rows].cpu().double()
+            Or, Lr = per_stream[si][-1]
+            assert torch.allclose(o, Or, atol=2e-5, rtol=1e-4)
+            fin = ~torch.isinf(Lr)
+            assert torch.equal(torch.isinf(l), torch.isinf(Lr)) and torch.allclose(l[fin], Lr[fin], atol=2e-5, rtol=1e-5)
+    att = rnd(rows, dh, seed=7).float().contiguous()
+    gates = (1.0, 0.5)
+    srcs = []
+    for si in range(2):
+        o = gathered[si * rows * (dh + 1):]
+        srcs.append((o, o[rows * dh:], world, 1, block, block, gates[si]))
+    out = torch.empty(rows, dh, device="cuda", dtype=BF)
+    ops.xattn_merge2(srcs, att, out, rows, dh)
+    ref = att.cpu().double() + sum(gates[si] * _merge_ref(per_stream[si])[0] for si in range(2))
+    assert rel_err(out.cpu().double(), ref) < 4e-3
+    assert not torch.isnan(gathered[:world * block]).any()          # every block fully written
+
+
+def test_peer_exchange_single_process_group():
+    """PartialExchange.local_group: `world` arenas on one device; every fake rank pushes its reduced partials into every arena and
+    publishes its sequence number; merge (with the flag wait) on every rank gives the same bits and matches the fp64 reference.
+    Run for several consecutive exchanges so that both slots and the sequence comparison are exercised."""
+    from vidi_b200 import ops
+    from vidi_b200.exchange import PartialExchange
+    world, rows, dh = 4, 40, 256
+    xs = PartialExchange.local_group(world, PartialExchange.capacity(rows, dh))
+    for step in range(5):
+        per_stream = [[], []]
+        all_srcs = []
+        for r in range(world):
+            srcs = []
+            for si, P in enumerate((3 + r, 1 + (r + step) % 3)):
+                O = rnd(P, rows, dh, seed=1000 * step + 10 * r + si).float().contiguous()
+                Ls = (2.0 * rnd(P, rows, seed=5000 + 1000 * step + 10 * r + si)).float().contiguous()
+                if r == 2 and si == 0:
+                    Ls[:] = float("-inf")
+                srcs.append((O, Ls, P))
+                per_stream[si].append(_merge_ref([(O[p].cpu(), Ls[p].cpu()) for p in range(P)]))
+            all_srcs.append(srcs)
+        for r in range(world):
+            assert ops.xchg_push(xs[r], all_srcs[r], rows, dh) == step + 1
+        att = rnd(rows, dh, seed=step).float().contiguous()
+        outs = []
+        for r in range(world):
+            out = torch.empty(rows, dh, device="cuda", dtype=BF)
+            ops.xchg_merge(xs[r], (1.0, 1.0), att, out, rows, dh)
+            outs.append(out)
+        torch.cuda.synchronize()
+        for x in xs:
+            x.check()
+        ref = att.cpu().double() + sum(_merge_ref(per_stream[si])[0] for si in range(2))
+        assert rel_err(outs[0].cpu().double(), ref) < 4e-3
+        assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+def test_peer_exchange_missing_peer_sets_error_flag():
+    """A rank that never publishes must surface as an error (bounded spin), not as a hung GPU."""
+    from vidi_b200 import ops
+    from vidi_b200.exchange import PartialExchange
+    world, rows, dh = 2, 8, 128
+    xs = PartialExchange.local_group(world, PartialExchange.capacity(rows, dh))
+    O = rnd(2, rows, dh, seed=1).float().contiguous(); Ls = rnd(2, rows, seed=2).float().contiguous()
+    ops.xchg_push(xs[0], [(O, Ls, 2)], rows, dh)          # rank 1 never pushes
+    att = rnd(rows, dh, seed=3).float().contiguous()
+    out = torch.empty(rows, dh, device="cuda", dtype=BF)
+    ops.xchg_merge(xs[0], (1.0,), att, out, rows, dh)
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="never delivered"):
+        xs[0].check()

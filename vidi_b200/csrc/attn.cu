@@ -522,11 +522,26 @@ struct MergeSrc {
 };
 __global__ void __launch_bounds__(128)
 xattn_merge2_kernel(MergeSrc s0, MergeSrc s1, int nsrc, const float* __restrict__ att, int rows, int DH,
-                    __nv_bfloat16* __restrict__ out) {
+                    __nv_bfloat16* __restrict__ out, const unsigned int* flags, int nflags, unsigned int seq, int* err) {
     const int row = blockIdx.x;
     extern __shared__ float wts2[];               // [P0 + P1]
     __shared__ float red[4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (flags != nullptr) {
+        // receive side of the peer-memory exchange (xchg.cu): wait until every rank's partial of this exchange has landed in
+        // this GPU's buffer.  Flags carry a monotonically increasing sequence number; a bounded spin turns a dead peer into an
+        // error flag instead of a hung GPU.
+        if (tid < nflags) {
+            const long long t0 = clock64();
+            while (true) {
+                unsigned int v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + tid) : "memory");
+                if ((int)(v - seq) >= 0) break;
+                if (clock64() - t0 > 6000000000ll) { atomicExch(err, 1); break; }
+            }
+        }
+        __syncthreads();
+    }
     float inv[2] = {0.f, 0.f};
     int base = 0;
     for (int si = 0; si < nsrc; ++si) {
@@ -534,7 +549,7 @@ xattn_merge2_kernel(MergeSrc s0, MergeSrc s1, int nsrc, const float* __restrict_
         float* w = wts2 + base;
         float lmax = -INFINITY;
         for (int p = tid; p < s.P; p += 128) {
-            const float l = s.L[(p / s.spr) * s.rsl + (int64_t)(p % s.spr) * rows + row];
+            const float l = __ldcg(s.L + (p / s.spr) * s.rsl + (int64_t)(p % s.spr) * rows + row);
             w[p] = l; lmax = fmaxf(lmax, l);
         }
         lmax = warp_max(lmax);
@@ -565,7 +580,7 @@ xattn_merge2_kernel(MergeSrc s0, MergeSrc s1, int nsrc, const float* __restrict_
             float2 a = make_float2(0.f, 0.f);
 #pragma unroll 4
             for (int p = 0; p < s.P; ++p) {
-                const float2 v = *reinterpret_cast<const float2*>(s.O + (p / s.spr) * s.rso + ((int64_t)(p % s.spr) * rows + row) * DH + c);
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(s.O + (p / s.spr) * s.rso + ((int64_t)(p % s.spr) * rows + row) * DH + c));
                 a.x += w[p] * v.x; a.y += w[p] * v.y;
             }
             acc.x += a.x * inv[si]; acc.y += a.y * inv[si];
@@ -691,12 +706,15 @@ int text_qk_prep(const void* qkv, int64_t ld, void* q_rope, int64_t ldq, void* k
 
 int xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0, const float* O1,
                  const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
-                 int rows, int dh, void* out_bf16, cudaStream_t st) {
+                 int rows, int dh, void* out_bf16, const unsigned int* flags, int nflags, unsigned int seq, int* err,
+                 cudaStream_t st) {
     if (rows == 0) return 0;
     VB_REQUIRE(nsrc >= 0 && nsrc <= 2 && dh % 2 == 0, "xattn_merge2: nsrc=%d dh=%d", nsrc, dh);
+    VB_REQUIRE(flags == nullptr || (nflags >= 1 && nflags <= 128 && err != nullptr), "xattn_merge2: bad flag arguments (nflags=%d)", nflags);
     MergeSrc s0{O0, L0, nsrc > 0 ? P0 : 0, spr0 > 0 ? spr0 : 1, rso0, rsl0, gate0};
     MergeSrc s1{O1, L1, nsrc > 1 ? P1 : 0, spr1 > 0 ? spr1 : 1, rso1, rsl1, gate1};
-    xattn_merge2_kernel<<<rows, 128, (s0.P + s1.P + 1) * sizeof(float), st>>>(s0, s1, nsrc, att, rows, dh, (__nv_bfloat16*)out_bf16);
+    xattn_merge2_kernel<<<rows, 128, (s0.P + s1.P + 1) * sizeof(float), st>>>(s0, s1, nsrc, att, rows, dh, (__nv_bfloat16*)out_bf16,
+                                                                              flags, nflags, seq, err);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -46,7 +46,13 @@ int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int
 int rope_inplace(void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int text_qk_prep(const void*, int64_t, void*, int64_t, void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int xattn_merge2(const float*, const float*, int, int, int64_t, int64_t, float, const float*, const float*, int, int, int64_t, int64_t,
-                 float, int, const float*, int, int, void*, cudaStream_t);
+                 float, int, const float*, int, int, void*, const unsigned int*, int, unsigned int, int*, cudaStream_t);
+int xattn_premerge_push(const float*, const float*, int, const float*, const float*, int, int, int, int, float* const*,
+                        unsigned int* const*, int, int64_t, unsigned int, unsigned int*, cudaStream_t);
+int p2p_alloc(int64_t, void**, void*);
+int p2p_open(const void*, void**);
+int p2p_close(void*);
+int p2p_free(void*);
 int attn_text(const void*, int64_t, const void*, const void*, int64_t, int, int, int, int, int, int, float, float, int, float*,
               cudaStream_t);
 }  // namespace vb
@@ -58,7 +64,7 @@ static std::atomic<int64_t> g_launches{0};
 extern "C" {
 
 const char* vidi_last_error(void) { return vb::last_error(); }
-int vidi_abi_version(void) { return 1; }
+int vidi_abi_version(void) { return 2; }
 int64_t vidi_launch_count(void) { return g_launches.load(); }
 void vidi_reset_launch_count(void) { g_launches.store(0); }
 
@@ -200,8 +206,25 @@ int vidi_xattn_merge2(const float* O0, const float* L0, int P0, int spr0, int64_
                       const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc, const float* att,
                       int rows, int dh, void* out_bf16, void* stream) {
     return COUNT(vb::xattn_merge2(O0, L0, P0, spr0, rso0, rsl0, gate0, O1, L1, P1, spr1, rso1, rsl1, gate1, nsrc, att, rows, dh,
-                                  out_bf16, ST(stream)));
+                                  out_bf16, nullptr, 0, 0u, nullptr, ST(stream)));
 }
+int vidi_xattn_merge2_sync(const float* O0, const float* L0, int P0, int spr0, int64_t rso0, int64_t rsl0, float gate0,
+                           const float* O1, const float* L1, int P1, int spr1, int64_t rso1, int64_t rsl1, float gate1, int nsrc,
+                           const float* att, int rows, int dh, void* out_bf16, const uint32_t* flags, int nflags, uint32_t seq,
+                           int* err, void* stream) {
+    return COUNT(vb::xattn_merge2(O0, L0, P0, spr0, rso0, rsl0, gate0, O1, L1, P1, spr1, rso1, rsl1, gate1, nsrc, att, rows, dh,
+                                  out_bf16, flags, nflags, seq, err, ST(stream)));
+}
+int vidi_xattn_premerge_push(const float* O0, const float* L0, int P0, const float* O1, const float* L1, int P1, int nsrc, int rows,
+                             int dh, float* const* peer_base, uint32_t* const* peer_flag, int world, int64_t my_block_off,
+                             uint32_t seq, uint32_t* counter, void* stream) {
+    return COUNT(vb::xattn_premerge_push(O0, L0, P0, O1, L1, P1, nsrc, rows, dh, peer_base, peer_flag, world, my_block_off, seq,
+                                         counter, ST(stream)));
+}
+int vidi_p2p_alloc(int64_t bytes, void** ptr, void* handle) { return vb::p2p_alloc(bytes, ptr, handle); }
+int vidi_p2p_open(const void* handle, void** ptr) { return vb::p2p_open(handle, ptr); }
+int vidi_p2p_close(void* ptr) { return vb::p2p_close(ptr); }
+int vidi_p2p_free(void* ptr) { return vb::p2p_free(ptr); }
 int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh, const float* inv_freq, int pos0, void* stream) {
     return COUNT(vb::rope_inplace(x, ld, col_off, T, heads, dh, inv_freq, pos0, ST(stream)));
 }

@@ -8,6 +8,8 @@
 //     address); tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs;
 //   * each CTA drains its own 128 TMEM lanes with the shared epilogue; the follower's epilogue threads release the
 //     accumulator on the leader's barrier through a shared::cluster arrive.
+#include <cstdlib>
+
 #include "gemm_epilogue.cuh"
 
 namespace vb {
@@ -62,6 +64,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+// the accumulator hand-back only has to order the tcgen05.ld's (already complete after tcgen05.wait::ld + the before_thread_sync fence);
+// a release at cluster scope would also wait for this thread's outstanding global stores (shows up as MEMBAR stalls in ncu)
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
@@ -191,7 +198,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
             epilogue_tile<BLOCK_N, LN>(p, taddr, row, n_blk, wg);
             tc_fence_before();
-            mbar_arrive_leader(&tmem_empty[acc]);
+            if (p.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty[acc]);
+            else mbar_arrive_leader(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -240,6 +248,8 @@ int gemm2_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual); p.ldr = ldr; p.res_mod = res_mod;
     p.act = act; p.act_param = act_param; p.out_fp32 = out_fp32; p.glu = glu;
+    static const int relaxed = getenv("VIDI_GEMM2_RELAXED") ? atoi(getenv("VIDI_GEMM2_RELAXED")) : 0;
+    p.relaxed_arrive = relaxed;
     if (ln_stats || stats_out) VB_REQUIRE(!glu && !out_fp32, "gemm2_bf16_ln: LayerNorm fold / row statistics need a plain bf16 output");
     if (ln_stats) {
         VB_REQUIRE(ln_parts > 0 && ln_colsum != nullptr, "gemm2_bf16_ln: ln_stats needs ln_parts > 0 and ln_colsum");

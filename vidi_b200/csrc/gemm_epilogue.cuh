@@ -32,6 +32,7 @@ struct GemmParams {
     // per-row (sum, sumsq) of the bf16 values this GEMM stores, one pair per (column tile, column half): [M, 2*num_n_tiles]
     float2* stats_out = nullptr;
     int stats_parts = 0;
+    int relaxed_arrive = 0;              // A/B: release the accumulator with a relaxed (not release.cluster) arrive
 };
 
 // taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;

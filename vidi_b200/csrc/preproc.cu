@@ -52,7 +52,8 @@ __global__ void resample_u8_to_chw_bf16_kernel(const uint8_t* __restrict__ src, 
         const int nmax = in_h - ymin[y];
         int acc = 1 << (kPilPrecisionBits - 1);
         for (int t = 0; t < ksize && t < nmax; ++t) acc += (int)s[(int64_t)t * row_stride] * k[t];
-        const float v = ((float)pil_clip8(acc) * rescale - mean) / stdv;       // same fp32 operation order as the HF processor
+        // three separately rounded fp32 operations, as the HF processor does them (no FMA contraction: it changes the bf16 result)
+        const float v = __fdiv_rn(__fsub_rn(__fmul_rn((float)pil_clip8(acc), rescale), mean), stdv);
         dst[(((int64_t)f * 3 + c) * out_h + y) * W + x] = __float2bfloat16(v);
     }
 }

@@ -82,12 +82,28 @@ def make_plan(cfg, n_frames: int, n_chunks: int, audio_size: int, rank: int = 0,
 
 class Vidi15Engine:
     def __init__(self, cfg, state_dict: dict, device="cuda", rank: int = 0, world: int = 1, group=None,
-                 pop_state_dict: bool = False, vit_chunk: int = 128, aud_chunk: int = 16):
+                 pop_state_dict: bool = False, vit_chunk: int = 128, aud_chunk: int = 16, exchange: str = "auto",
+                 max_text_rows: int = 256):
         if not torch.cuda.is_available():
             raise RuntimeError("vidi_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.cfg = cfg
         self.device = torch.device(device)
         self.rank, self.world, self.group = rank, world, group
+        # Multi-rank text pass: (O, LSE) partials cross ranks through peer-mapped arenas ("p2p", csrc/xchg.cu) -- or, when the arenas
+        # cannot be mapped (or exchange="nccl"), through one NCCL all-gather per layer.  Both are GPU paths with identical results.
+        self.xchg, self.exchange_note = None, "single rank"
+        if world > 1:
+            self.exchange_note = "nccl all-gather of the per-rank reduced (O, LSE) blocks"
+            if exchange in ("auto", "p2p"):
+                from .exchange import PartialExchange
+                try:
+                    self.xchg = PartialExchange.connect(rank, world, group, PartialExchange.capacity(max_text_rows * cfg.llm.heads, cfg.llm.head_dim),
+                                                        self.device)
+                    self.exchange_note = "peer-memory stores over NVLink + flag wait (no collective call)"
+                except RuntimeError as ex:
+                    if exchange == "p2p":
+                        raise
+                    self.exchange_note += f" (peer arenas unavailable: {ex})"
         self.W = load_vidi15(state_dict, cfg, self.device, ops, pop=pop_state_dict)
         # Gemma2 family (Vidi1.5) vs Mistral family (Vidi-7B): SURVEY.md 3.3
         self.gemma = hasattr(cfg.llm, "final_softcap")
@@ -362,6 +378,8 @@ class Vidi15Engine:
         else:
             kv = self.stream_pass(S)
             logits = self.text_pass(ids, kv, seg, text_cache=text_cache, logits_to_keep=logits_to_keep)
+        if self.xchg is not None:
+            self.xchg.check()
         if return_state:
             return logits, dict(kv=kv, seg=seg, plan=plan, streams=S)
         return logits
@@ -390,12 +408,22 @@ class _TextRun:
         self.h = ops.rmsnorm(self.H, Ls[0].n_in, c.rms_eps, gm)
         self.rows = self.Tq * c.heads
         dh = c.head_dim
-        # one flat fp32 buffer per layer holds every stream's [O | LSE] partials of this rank
+        # one flat fp32 buffer per layer holds every stream's [O | LSE] split partials of this rank
         self.splits = [ops.xattn_splits(-(-s[4] // eng.world), c.kv_heads, eng.n_sms) for s in seg]
         self.sizes = [sp * self.rows * (dh + 1) for sp in self.splits]
         self.flat = torch.empty(max(1, sum(self.sizes)), device=eng.device, dtype=torch.float32)
-        self.gathered = (torch.empty(eng.world * self.flat.numel(), device=eng.device, dtype=torch.float32)
-                         if eng.world > 1 else self.flat)
+        # multi-rank: each rank first reduces its own splits to ONE (O, LSE) partial per stream (xchg.cu), and only those cross ranks:
+        #   "p2p"  -- stored straight into every peer's arena over NVLink, merge kernel waits on flags (no NCCL, no host sync)
+        #   "nccl" -- one all_gather_into_tensor of the reduced block per layer (used when the arenas cannot be mapped)
+        self.mode = "local"
+        if eng.world > 1 and seg:
+            x = eng.xchg
+            self.mode = "p2p" if (x is not None and x.fits(len(seg), self.rows, dh)) else "nccl"
+            if self.mode == "nccl":
+                assert eng.group is not None or torch.distributed.is_initialized(), "multi-rank text pass needs a process group or a peer arena"
+                self.block = len(seg) * self.rows * (dh + 1)
+                self.pre = torch.empty(self.block, device=eng.device, dtype=torch.float32)
+                self.gathered = torch.empty(eng.world * self.block, device=eng.device, dtype=torch.float32)
         self.att = torch.empty(self.Tq, c.q_dim, device=eng.device, dtype=torch.float32)
         self.y = torch.empty(self.Tq, c.hidden, device=eng.device, dtype=BF16)
         self.h2 = torch.empty_like(self.H)
@@ -404,10 +432,14 @@ class _TextRun:
         self.krope = torch.empty(self.Tq, 2 * c.kv_dim, device=eng.device, dtype=BF16) if text_cache is None else None
 
     def layer(self, l: int):
+        self.layer_begin(l)
+        self.layer_end(l)
+
+    def layer_begin(self, l: int):
+        """text self-attention + this rank's cross-attention partials of layer l, sent on their way to the peers"""
         e, c = self.e, self.c
         gm = e.gemma
-        Ls = e.W.layers
-        L = Ls[l]
+        L = e.W.layers[l]
         Tq, pos0, rows = self.Tq, self.pos0, self.rows
         qd, kd, dh = c.q_dim, c.kv_dim, c.head_dim
         qkv = ops.gemm(self.h, L.wqkv, tag="text")
@@ -423,21 +455,43 @@ class _TextRun:
         ops.attn_text(self.qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, self.scale, self.cap, window, out=self.att)
         off = 0
         kvl = self.kv[l]
+        srcs = []
         for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
             op = self.flat[off:off + sp * rows * dh]
             ls = self.flat[off + sp * rows * dh:off + sz]
             ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
                               self.scale, self.cap, sp, opart=op, lse=ls)
+            srcs.append((op, ls, sp))
             off += sz
-        if e.world > 1 and self.seg:
-            torch.distributed.all_gather_into_tensor(self.gathered, self.flat, group=e.group)
+        if self.mode == "p2p":
+            ops.xchg_push(e.xchg, srcs, rows, dh)
+        elif self.mode == "nccl":
+            ops.xattn_premerge(srcs, rows, dh, self.pre)
+            torch.distributed.all_gather_into_tensor(self.gathered, self.pre, group=e.group)
+
+    def layer_end(self, l: int):
+        """merge the partials of all ranks, o_proj, residual + MLP of layer l"""
+        e, c = self.e, self.c
+        gm = e.gemma
+        Ls = e.W.layers
+        L = Ls[l]
+        rows, dh = self.rows, c.head_dim
+        gates = [s[3] for s in self.seg]
         # one launch: a = bf16(att_text + gate_img * merge(img partials) + gate_aud * merge(aud partials))
-        srcs, off = [], 0
-        for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
-            srcs.append((self.gathered[off:], self.gathered[off + sp * rows * dh:], e.world * sp, sp, self.flat.numel(),
-                         self.flat.numel(), gate))
-            off += sz
-        a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
+        if self.mode == "p2p":
+            a = ops.xchg_merge(e.xchg, gates, self.att, self.a, rows, dh)
+        elif self.mode == "nccl":
+            srcs = []
+            for si, gate in enumerate(gates):
+                o = self.gathered[si * rows * (dh + 1):]
+                srcs.append((o, o[rows * dh:], e.world, 1, self.block, self.block, gate))
+            a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
+        else:
+            srcs, off = [], 0
+            for gate, sp, sz in zip(gates, self.splits, self.sizes):
+                srcs.append((self.flat[off:], self.flat[off + sp * rows * dh:], sp, sp, 0, 0, gate))
+                off += sz
+            a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
         ops.gemm(a, L.wo, out=self.y, tag="text")
         w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else e.W.final_norm
         if gm:

@@ -51,6 +51,12 @@ SIGNATURES = {
     "vidi_xattn_merge": [_p, _p, _i, _i, _l, _l, _i, _i, _f, _i, _p, _p],
     "vidi_text_qk_prep": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _p, _i, _p],
     "vidi_xattn_merge2": [_p, _p, _i, _i, _l, _l, _f, _p, _p, _i, _i, _l, _l, _f, _i, _p, _i, _i, _p, _p],
+    "vidi_xattn_merge2_sync": [_p, _p, _i, _i, _l, _l, _f, _p, _p, _i, _i, _l, _l, _f, _i, _p, _i, _i, _p, _p, _i, C.c_uint32, _p, _p],
+    "vidi_xattn_premerge_push": [_p, _p, _i, _p, _p, _i, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _i, _l, C.c_uint32, _p, _p],
+    "vidi_p2p_alloc": [_l, C.POINTER(_p), _p],
+    "vidi_p2p_open": [_p, C.POINTER(_p)],
+    "vidi_p2p_close": [_p],
+    "vidi_p2p_free": [_p],
     "vidi_rope_inplace": [_p, _l, _i, _i, _i, _i, _p, _i, _p],
     "vidi_attn_text": [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p],
 }

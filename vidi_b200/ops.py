@@ -377,6 +377,31 @@ def xattn_merge2(srcs, att, out_bf16, rows: int, dh: int):
     return out_bf16
 
 
+def xattn_premerge(srcs, rows: int, dh: int, out: torch.Tensor):
+    """srcs: [(O [P,rows,dh] f32, LSE [P,rows] f32, P)] per stream -> out fp32 flat [per stream: O [rows,dh] | LSE [rows]]: this rank's
+    key splits reduced to one partial per stream (what crosses ranks; csrc/xchg.cu)."""
+    L = _lib.load()
+    assert 1 <= len(srcs) <= 2 and out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= len(srcs) * rows * (dh + 1)
+    s0 = srcs[0]
+    s1 = srcs[1] if len(srcs) > 1 else (None, None, 0)
+    base = (C.c_void_p * 1)(out.data_ptr())
+    _lib.check(L.vidi_xattn_premerge_push(_ptr(s0[0]), _ptr(s0[1]), s0[2], _ptr(s1[0]), _ptr(s1[1]), s1[2], len(srcs), rows, dh, base,
+                                          None, 1, 0, 0, None, _stream()), "xattn_premerge_push")
+    return out
+
+
+def xchg_push(xchg, srcs, rows: int, dh: int) -> int:
+    """send side of the peer-memory exchange (exchange.PartialExchange.push) on the current stream"""
+    return xchg.push([(_ptr(o), _ptr(l), p) for o, l, p in srcs], rows, dh, _stream())
+
+
+def xchg_merge(xchg, gates, att, out_bf16, rows: int, dh: int):
+    """receive side: waits for every rank's partial of the current exchange, then out = bf16(att + sum_s gate_s * merge_s)"""
+    assert att.dtype == torch.float32 and out_bf16.dtype == BF16 and att.is_cuda
+    xchg.merge(gates, att, out_bf16, rows, dh, _stream())
+    return out_bf16
+
+
 def rope_inplace(x, col_off: int, heads: int, dh: int, inv_freq, pos0: int = 0):
     L = _lib.load()
     T = x.shape[0]
@@ -430,7 +455,8 @@ def _instrument(fn):
 
 for _name in ("rmsnorm", "residual_norm", "layernorm", "mm_finish", "rmsnorm_f32", "patch_im2col", "whisper_im2col1",
               "whisper_im2col2", "pool_s2d", "conv_window_gather", "bilinear_ac", "embed_gather", "sinusoid_split", "split3",
-              "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text", "text_qk_prep", "xattn_merge2"):
+              "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text", "text_qk_prep", "xattn_merge2",
+              "xattn_premerge", "xchg_push", "xchg_merge"):
     globals()[_name] = _instrument(globals()[_name])
 
 
