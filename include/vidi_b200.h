@@ -181,6 +181,66 @@ int vidi_rope_inplace(void* x, int64_t ld, int col_off, int T, int heads, int dh
 int vidi_attn_text(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int Tq, int Tk, int pos0, int Hq,
                    int Hkv, int dh, float scale, float softcap, int window, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * The whole text stream of one prefill / decode step in ONE call: every decoder layer's T2T self attention, T2V / T2A split-KV
+ * cross attention against the image / audio K||V cache, the (multi-GPU) exchange of the partials, o_proj, the norms and the GLU
+ * MLP, then the final norm and lm_head -- DattnGemma2Model.forward's layer loop for the text rows (gemma.py:362-409 with
+ * :160-175, :185-192, :206-221, :236-238, :411, :564-569; Mistral family: Vidi_7B mistral.py:190-264, 615-616).  The reference
+ * issues these as ~40 eager PyTorch ops per layer; here a native loop enqueues 12 kernels per layer on `stream` with no Python in
+ * between, which is what makes decode (Tq = 1) and the replicated text pass of the multi-GPU prefill launch-latency free.
+ * All pointers are device pointers except layer_w (HOST array).  Nothing is synchronised. */
+typedef struct VidiTextLayerW {
+    const void* wqkv;     /* bf16 [heads*head_dim + 2*kv_heads*head_dim, hidden]   q | k | v rows                           */
+    const void* wo;       /* bf16 [hidden, heads*head_dim]                                                                  */
+    const void* wgu;      /* bf16 [2*inter, hidden], gate/up rows interleaved per 256-row tile (weights.pack_glu)           */
+    const void* wd;       /* bf16 [hidden, inter]                                                                           */
+    const void* n_in;     /* bf16 [hidden] input_layernorm                                                                  */
+    const void* n_post;   /* bf16 [hidden] post_attention_layernorm                                                         */
+    const void* n_preff;  /* bf16 [hidden] pre_feedforward_layernorm  (Gemma2 family; NULL for Mistral)                     */
+    const void* n_postff; /* bf16 [hidden] post_feedforward_layernorm (Gemma2 family; NULL for Mistral)                     */
+} VidiTextLayerW;
+typedef struct VidiTextSeg {
+    int64_t row0;          /* first row of this stream (image or audio) in the K||V cache of every layer                    */
+    int32_t rows;          /* keys of this stream held by this rank (may be 0)                                              */
+    int32_t splits;        /* key splits (>= 1)                                                                             */
+    const uint8_t* kmask;  /* uint8 [rows] key-padding mask or NULL                                                         */
+    float gate;            /* `any(mask)` gate of gemma.py:192 as 1.0 / 0.0                                                 */
+    int32_t reserved;
+} VidiTextSeg;
+typedef struct VidiTextPass {
+    int32_t Tq, pos0, layers, hidden, heads, kv_heads, head_dim, inter, vocab;
+    int32_t gemma;           /* 1: Gemma2 family (post norms, soft-caps, (1+w) norms, alternating window); 0: Mistral family */
+    int32_t glu;             /* VIDI_GLU_GELU_TANH / VIDI_GLU_SILU                                                          */
+    int32_t sliding_window;  /* Gemma2: applied on even layers; Mistral: on every layer; 0 = none                           */
+    int32_t logits_keep;     /* 0: logits for all Tq rows, k: for the last k rows                                           */
+    float rms_eps, scale, attn_softcap, final_softcap, normalizer;
+    const VidiTextLayerW* layer_w;   /* HOST array [layers] */
+    const void* embed;       /* bf16 [vocab, hidden] */
+    const void* final_norm;  /* bf16 [hidden] */
+    const void* lm_head;     /* bf16 [vocab, hidden] */
+    const float* inv_freq;   /* fp32 [head_dim/2] */
+    const int64_t* ids;      /* int64 [Tq], sentinel already stripped */
+    void* text_kv;           /* bf16 [layers][max_len][2*kv_dim] text K||V cache (rows pos0..pos0+Tq are written), or NULL when
+                                pos0 == 0 and nothing is kept (scratch from the workspace is used)                          */
+    int64_t text_kv_layer_stride, text_kv_ld;    /* in elements */
+    const void* stream_kv;   /* bf16 [layers][N][2*kv_dim] image+audio K||V cache of this rank */
+    int64_t stream_layer_stride, stream_ld;      /* in elements */
+    int32_t nseg;
+    int32_t world, rank;     /* world > 1: partials cross ranks through the peer arenas below (see vidi_xattn_premerge_push) */
+    uint32_t seq0;           /* sequence number of the last exchange issued before this call; layer l uses seq0 + l + 1     */
+    VidiTextSeg seg[2];
+    float* peer_data[16];    /* arena data base of every rank (peer-mapped): fp32 [2 slots][world][cap]                      */
+    uint32_t* peer_flags[16];/* arena flag base of every rank: uint32 [2 slots][world]                                      */
+    int64_t cap;             /* floats per rank block */
+    uint32_t* counter;       /* one zero-initialised uint32 on this device */
+    int32_t* err;            /* set to 1 if a peer never delivered */
+    void* workspace;         /* >= vidi_text_pass_workspace_bytes() bytes, 256-byte aligned */
+    int64_t workspace_bytes;
+    float* logits;           /* fp32 [logits_keep ? logits_keep : Tq][vocab] */
+} VidiTextPass;
+int64_t vidi_text_pass_workspace_bytes(const VidiTextPass* d);
+int vidi_text_pass(const VidiTextPass* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -351,7 +351,7 @@ def prefill(sd, cfg, input_ids, images: Optional[torch.Tensor], mels: Optional[t
 
 @torch.no_grad()
 def greedy_generate(sd, cfg, input_ids, images, mels, audio_size, max_new_tokens=8, eos_id=107,
-                    normalizer_dtype=torch.float32):
+                    normalizer_dtype=torch.float32, return_margins=False):
     """Greedy decode by full re-prefill of the text (the streams do not depend on text, so the
     image/audio K,V are computed once).  Matches generate(do_sample=False) (gemma.py:603-655)."""
     c = cfg.llm
@@ -371,7 +371,7 @@ def greedy_generate(sd, cfg, input_ids, images, mels, audio_size, max_new_tokens
             kvs.append((K, V, st[1])); st[0] = S_next
         kv_layers.append(kvs)
     W = sd["model.embed_tokens.weight"] if c.tie_word_embeddings else sd["lm_head.weight"]
-    out = []
+    out, margins = [], []       # margins: top-1 minus top-2 logit of every step (tests pick fixtures with decisive margins)
     for _ in range(max_new_tokens):
         T = ids.shape[0]
         H = sd["model.embed_tokens.weight"].float()[ids] * nrm
@@ -381,7 +381,9 @@ def greedy_generate(sd, cfg, input_ids, images, mels, audio_size, max_new_tokens
         logit = softcap(linear(gemma_norm(H[-1:], sd["model.norm.weight"], c.rms_eps), W), c.final_softcap)
         nxt = int(logit.argmax(-1))
         out.append(nxt)
+        t2 = logit[0].topk(2).values
+        margins.append(float(t2[0] - t2[1]))
         if nxt == eos_id:
             break
         ids = torch.cat([ids, torch.tensor([nxt])])
-    return out
+    return (out, margins) if return_margins else out

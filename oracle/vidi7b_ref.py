@@ -137,3 +137,19 @@ def prefill(sd, cfg, input_ids, images, mels, audio_size, return_intermediates=F
         Hn = Hn[-logits_to_keep:]
     logits = linear(Hn, sd["lm_head.weight"])
     return (logits, inter) if return_intermediates else logits
+
+
+def greedy_generate(sd, cfg, input_ids, images, mels, audio_size, max_new_tokens=8, eos_id=2, return_margins=False):
+    """Greedy decode by full re-prefill (DattnMistralForCausalLM.generate with do_sample=False, mistral.py:622-681).  Test
+    infrastructure: quadratic, for mini dims only."""
+    ids = input_ids.clone()
+    out, margins = [], []
+    for _ in range(max_new_tokens):
+        logit = prefill(sd, cfg, ids, images, mels, audio_size, logits_to_keep=1)[-1]
+        t2 = logit.topk(2).values
+        nxt = int(logit.argmax(-1))
+        out.append(nxt); margins.append(float(t2[0] - t2[1]))
+        if nxt == eos_id:
+            break
+        ids = torch.cat([ids, torch.tensor([nxt])])
+    return (out, margins) if return_margins else out

@@ -46,7 +46,7 @@ def main():
     else:
         # BASELINE config 3's shape at true 9B hidden dims with the depth cut: the 10x10 feature-map floor of the resize branch
         # (multimodal.py:175-180), >= 2 audio chunks per rank, uneven frame split
-        cfg = dataclasses.replace(vidi15_true_dims(llm_layers=3, vis_layers=2, aud_layers=1, vocab=4096), max_image_tokens=500)
+        cfg = dataclasses.replace(vidi15_true_dims(llm_layers=3, vis_layers=2, aud_layers=1, vocab=4096), max_image_tokens=300)
         F, Cn, n_text = 4 * world + 5, 2 * world + 1, 32
         asz = Cn * 3000 - 900
         assert cfg.image_hw(F) == (10, 10), cfg.image_hw(F)

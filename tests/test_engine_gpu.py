@@ -195,6 +195,38 @@ def test_multirank_text_path_lockstep_equals_single_rank(world, F, Cn, asz):
     assert torch.equal(outs[0].cpu().argmax(-1)[confident], ref.argmax(-1)[confident])
 
 
+@pytest.mark.parametrize("family", ["gemma", "mistral"])
+def test_native_text_pass_equals_per_layer_path(family):
+    """vidi_text_pass (csrc/textpass.cu, one C call for all layers) issues the same kernels with the same arguments as the per-layer
+    Python path: prefill logits, the text K||V cache it fills and three decode steps must be BIT-identical, for both model families,
+    with a key-padding mask in play (zero frame) and logits_to_keep."""
+    from oracle import synth
+    from vidi_b200.config import vidi15_mini, vidi7b_mini
+    from vidi_b200.engine import Vidi15Engine
+    cfg = vidi15_mini(llm_layers=3) if family == "gemma" else vidi7b_mini(llm_layers=3)
+    sd = synth.make_state_dict(cfg, seed=77)
+    eng = Vidi15Engine(cfg, {k: (v if "mm_rand_pos" in k else v.to(BF)) for k, v in sd.items()}, device="cuda")
+    ids, images, mels, asz = synth.make_inputs(cfg, 4, 2, n_text=21, audio_size=4000)
+    images[1] = 0                                        # an all-zero frame -> masked keys (multimodal.py:202)
+    ids_dev = ids[ids != -200].cuda()
+    img, mel = images.cuda().to(BF), mels.cuda().to(BF)
+    outs = {}
+    for native in (False, True):
+        eng.native_text = native
+        tc = eng.new_text_cache(32)
+        lg, st = eng.prefill(ids_dev, img, mel, asz, text_cache=tc, logits_to_keep=5, return_state=True)
+        steps = [lg]
+        for tok in (17, 400, 3):
+            steps.append(eng.text_pass(torch.tensor([tok], device="cuda"), st["kv"], st["seg"], text_cache=tc, logits_to_keep=1))
+        no_cache = eng.text_pass(ids_dev, st["kv"], st["seg"])
+        outs[native] = (steps, tc["kv"][:, :tc["len"]].clone(), tc["len"], no_cache)
+    assert outs[True][2] == outs[False][2] == 21 + 3
+    assert torch.equal(outs[True][1], outs[False][1])
+    for a, b in zip(outs[True][0], outs[False][0]):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert outs[True][0][0].shape == (5, cfg.llm.vocab) and torch.equal(outs[True][3], outs[False][3])
+
+
 def test_vidi7b_prefill_mini():
     """Vidi-7B (Mistral Dattn): learned-conv pooling, SwiGLU, no post-norms / soft-caps, dh=128."""
     from oracle import synth, vidi7b_ref as R7
@@ -246,11 +278,9 @@ def test_facade_forward_generate_match_oracle():
     n_new = 6
     gen = model.generate(ids[None], images=images[None], audios=mels[None], audio_sizes=[asz], do_sample=False,
                          max_new_tokens=n_new, use_cache=True, disable_compile=True, pad_token_id=0)
-    ref_ids = R.greedy_generate(sd, cfg, ids, images, mels, asz, max_new_tokens=n_new, normalizer_dtype=BF)
-    assert gen.shape[0] == 1 and gen.shape[1] <= n_new
-    g = gen[0].tolist()
-    assert g[0] == ref_ids[0]
-    assert g[:len(ref_ids)] == ref_ids[:len(g)] or sum(a == b for a, b in zip(g, ref_ids)) >= len(ref_ids) - 1
+    ref_ids, margins = R.greedy_generate(sd, cfg, ids, images, mels, asz, max_new_tokens=n_new, normalizer_dtype=BF, return_margins=True)
+    assert min(margins) > 1.0                          # decisive fixture (input seed 5): full equality is a fair demand
+    assert gen[0].tolist() == ref_ids                  # see tests/test_generate_gpu.py for a non-degenerate decode
     with pytest.raises(NotImplementedError):
         model.generate(ids[None], inputs_embeds=torch.zeros(1))
     with pytest.raises(ValueError):

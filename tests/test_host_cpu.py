@@ -185,3 +185,21 @@ def test_header_is_plain_c99_and_links_from_c(tmp_path):
     assert cc.returncode == 0, cc.stderr
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.startswith("abi="), (run.stdout, run.stderr)
+
+
+def test_text_pass_descriptor_layout_matches_the_c_compiler(tmp_path):
+    """lib.VidiTextPass / VidiTextLayerW / VidiTextSeg (ctypes) must have exactly the layout gcc gives the structs of
+    include/vidi_b200.h -- the descriptor crosses the C ABI by pointer."""
+    import ctypes as C
+    import subprocess
+    from vidi_b200.lib import VidiTextLayerW, VidiTextPass, VidiTextSeg
+    fields = [n for n, _ in VidiTextPass._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vidi_b200.h"\nint main(void){\n'
+                   'printf("%zu %zu %zu\\n", sizeof(VidiTextLayerW), sizeof(VidiTextSeg), sizeof(VidiTextPass));\n'
+                   + "".join(f'printf("%zu\\n", offsetof(VidiTextPass, {n}));\n' for n in fields) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out[:3]] == [C.sizeof(VidiTextLayerW), C.sizeof(VidiTextSeg), C.sizeof(VidiTextPass)]
+    assert [int(x) for x in out[3:]] == [getattr(VidiTextPass, n).offset for n in fields]

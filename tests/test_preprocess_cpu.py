@@ -126,3 +126,36 @@ def test_split_bf16_logmel_arithmetic_is_within_tolerance_of_hf():
     logs = torch.log10(mel.clamp(min=1e-10))[:-1].t()
     out = (torch.maximum(logs, logs.max() - 8.0) + 4.0) / 4.0
     assert float((out - ref).abs().max()) <= 5e-4
+
+
+def test_reference_process_images_call_pattern_with_facade_config():
+    """``process_images(video, image_processor, model.config)`` exactly as ask() calls it (inference.py:22, img_utils.py:173-198): the
+    function reads ``model_cfg.mm_image_aspect_ratio`` and raises NotImplementedError for anything it does not know, so the facade's
+    config must carry the key -- by default and when taken from a checkpoint's config.json.  The body below restates the reference's
+    'resize' branch against our processor (PIL in, dict out)."""
+    from PIL import Image
+    from vidi_b200.config import vidi15_mini, vidi7b_mini
+    from vidi_b200.model import config_from_hf_json, hf_like_config
+
+    def process_images(images, image_processor, model_cfg):
+        aspect = getattr(model_cfg, "mm_image_aspect_ratio", None)
+        if aspect != "resize":
+            raise NotImplementedError(f"Unsupported image aspect ratio: {aspect}")
+        out = []
+        for image in images:
+            image = image.resize((image_processor.output_size, image_processor.output_size), resample=Image.BICUBIC)
+            out.append(image_processor.preprocess(image, return_tensors="pt")["pixel_values"][0])
+        return torch.stack(out, 0)
+
+    g = torch.Generator().manual_seed(0)
+    frames = [Image.fromarray(torch.randint(0, 256, (90, 160, 3), generator=g, dtype=torch.uint8).numpy()) for _ in range(2)]
+    ip = SiglipImageProcessorLite(64)
+    for cfg in (vidi15_mini(), vidi7b_mini(), config_from_hf_json({}), config_from_hf_json({"model_type": "dattn_mistral"}),
+                config_from_hf_json({"mm_image_aspect_ratio": "resize", "mm_image_pool_size": None})):
+        mc = hf_like_config(cfg)
+        assert mc.mm_image_aspect_ratio == "resize"
+        video = process_images(frames, ip, mc)
+        assert video.shape == (2, 3, 64, 64) and video.dtype == torch.float32
+        mc.mm_splits = 32                                                  # stays a settable attribute (inference.py:86)
+    assert hf_like_config(config_from_hf_json({"model_type": "dattn_mistral"})).model_type == "dattn_mistral"
+    assert hf_like_config(config_from_hf_json({"model_type": "dattn_mistral"})).eos_token_id == 2

@@ -26,12 +26,17 @@ def main():
     ap.add_argument("--cta2", type=int, default=1)
     ap.add_argument("--no-attn", action="store_true")
     ap.add_argument("--tag", default="")
+    ap.add_argument("--bn", type=int, default=0, help="force the column tile of the four GEMMs (0 = ops.pick_block_n)")
+    ap.add_argument("--frames", type=int, default=0, help="frames (vit) / chunks (aud) per block; default 128 / 16")
     a = ap.parse_args()
     if a.tower == "vit":
         B, S, H, dh, d, ff, act = 128, 729, 16, 72, 1152, 4304, ops.ACT_GELU_TANH
     else:
         B, S, H, dh, d, ff, act = 16, 1500, 20, 64, 1280, 5120, ops.ACT_GELU_ERF
+    if a.frames:
+        B = a.frames
     M = B * S
+    bn = a.bn or None
     g = torch.Generator(device="cuda").manual_seed(0)
     rn = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc)
     x = rn(M, d).to(BF)
@@ -46,13 +51,13 @@ def main():
 
     def block():
         ops.layernorm(x, lw, lb, 1e-6, out=h)
-        ops.gemm(h, wqkv, bias=bqkv, out=qkv, tag="qkv", cta2=cta2)
+        ops.gemm(h, wqkv, bias=bqkv, out=qkv, tag="qkv", cta2=cta2, block_n=bn)
         if not a.no_attn:
             ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=att)
-        ops.gemm(att, wo, bias=bo, residual=x, out=x, tag="out", cta2=cta2)
+        ops.gemm(att, wo, bias=bo, residual=x, out=x, tag="out", cta2=cta2, block_n=bn)
         ops.layernorm(x, lw, lb, 1e-6, out=h)
-        ops.gemm(h, w1, bias=b1, act=act, out=m, tag="fc1", cta2=cta2)
-        ops.gemm(m, w2, bias=b2, residual=x, out=x, tag="fc2", cta2=cta2)
+        ops.gemm(h, w1, bias=b1, act=act, out=m, tag="fc1", cta2=cta2, block_n=bn)
+        ops.gemm(m, w2, bias=b2, residual=x, out=x, tag="fc2", cta2=cta2, block_n=bn)
 
     for _ in range(4):
         block()
@@ -61,14 +66,15 @@ def main():
     stop = False
 
     def sample():
+        import pynvml as nv
+        nv.nvmlInit()
+        hd = nv.nvmlDeviceGetHandleByIndex(0)
         while not stop:
             try:
-                o = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                clocks.append((float(o[0]), float(o[1])))
+                clocks.append((float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(hd) / 1000.0))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
     th = threading.Thread(target=sample, daemon=True)
     th.start()
     ops.PROFILE, ops.PROFILE_OPS = [], {}

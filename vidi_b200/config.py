@@ -105,6 +105,7 @@ class Vidi15Config:
     mm_eps: float = 1e-5                 # vidi/model/mm_layer/norm.py:9,19
     max_image_tokens: int = 60000        # multimodal.py:176
     mm_splits: int = 1                   # kept settable for drop-in (inference.py:86); ignored
+    mm_image_aspect_ratio: str = "resize"   # read by process_images(video, image_processor, model.config) (img_utils.py:173-198)
     name: str = "vidi1.5-9b"
 
     # ---- token math (multimodal.py:175-180, utils.py:152-171) ----
@@ -172,6 +173,7 @@ class MistralCfg:
     rms_eps: float = 1e-5
     rope_theta: float = 10000.0
     tie_word_embeddings: bool = False
+    sliding_window: int = 0          # MistralConfig.sliding_window (4096 in Mistral-7B-v0.1, null in v0.2+); 0 = full attention
 
     @property
     def q_dim(self) -> int:
@@ -197,6 +199,7 @@ class Vidi7BConfig:
     mm_std: float = 0.028976401314139366
     mm_eps: float = 1e-5
     mm_splits: int = 1
+    mm_image_aspect_ratio: str = "resize"
     name: str = "vidi-7b"
 
     def image_tokens(self, n_frames: int) -> int:

@@ -49,6 +49,8 @@ int xattn_merge2(const float*, const float*, int, int, int64_t, int64_t, float, 
                  float, int, const float*, int, int, void*, const unsigned int*, int, unsigned int, int*, cudaStream_t);
 int xattn_premerge_push(const float*, const float*, int, const float*, const float*, int, int, int, int, float* const*,
                         unsigned int* const*, int, int64_t, unsigned int, unsigned int*, cudaStream_t);
+int64_t text_pass_workspace_bytes(const VidiTextPass*);
+int text_pass(const VidiTextPass*, int64_t*, cudaStream_t);
 int p2p_alloc(int64_t, void**, void*);
 int p2p_open(const void*, void**);
 int p2p_close(void*);
@@ -220,6 +222,13 @@ int vidi_xattn_premerge_push(const float* O0, const float* L0, int P0, const flo
                              uint32_t seq, uint32_t* counter, void* stream) {
     return COUNT(vb::xattn_premerge_push(O0, L0, P0, O1, L1, P1, nsrc, rows, dh, peer_base, peer_flag, world, my_block_off, seq,
                                          counter, ST(stream)));
+}
+int64_t vidi_text_pass_workspace_bytes(const VidiTextPass* d) { return vb::text_pass_workspace_bytes(d); }
+int vidi_text_pass(const VidiTextPass* d, void* stream) {
+    int64_t n = 0;
+    const int rc = vb::text_pass(d, &n, ST(stream));
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    return rc;
 }
 int vidi_p2p_alloc(int64_t bytes, void** ptr, void* handle) { return vb::p2p_alloc(bytes, ptr, handle); }
 int vidi_p2p_open(const void* handle, void** ptr) { return vb::p2p_open(handle, ptr); }

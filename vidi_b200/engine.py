@@ -118,6 +118,13 @@ class Vidi15Engine:
         # persistent GEMMs delay those kernels' CTAs more than the hidden text latency is worth.  Kept off by default.
         self.overlap_text = False
         self.fold_ln = False         # see enable_ln_fold()
+        # diagnostic: added to the key-split count of the cross attention.  Results are mathematically identical for any split
+        # count; bench.py / the tests use it to measure the fp32 re-association noise floor that N-rank vs 1-rank comparisons
+        # of a 42-layer random-weight stack sit on.
+        self.split_bias = 0
+        # text stream through the native executor (csrc/textpass.cu: one C call per pass instead of ~500 ctypes launches); the
+        # per-layer Python path (_TextRun) stays for the side-stream overlap mode, the NCCL exchange and the lock-step tests
+        self.native_text = True
         self.vit_chunk, self.aud_chunk = vit_chunk, aud_chunk
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
 
@@ -316,10 +323,84 @@ class Vidi15Engine:
         """ids [Tq] int64 (sentinel already stripped) -> logits fp32 [Tq or k, vocab].
         seg: list of (row0, n_rows, kmask or None, gate, n_total) describing the image / audio row ranges of the
         local K||V cache.  (gemma.py:160-175, 185-192, 206-221, 236-238, 564-569)"""
+        if self.native_text and (self.world == 1 or (self.xchg is not None and self.xchg.fits(len(seg), ids.numel() * self.cfg.llm.heads,
+                                                                                              self.cfg.llm.head_dim))):
+            return self._text_pass_native(ids, kv, seg, text_cache, logits_to_keep)
         run = _TextRun(self, ids, kv, seg, text_cache, logits_to_keep)
         for l in range(len(self.W.layers)):
             run.layer(l)
         return run.finish()
+
+    def _layer_table(self):
+        """HOST array of per-layer weight pointers for vidi_text_pass (built once)"""
+        if getattr(self, "_ltab", None) is None:
+            from .lib import VidiTextLayerW
+            tab = (VidiTextLayerW * len(self.W.layers))()
+            for t, L in zip(tab, self.W.layers):
+                t.wqkv, t.wo, t.wgu, t.wd = L.wqkv.data_ptr(), L.wo.data_ptr(), L.wgu.data_ptr(), L.wd.data_ptr()
+                t.n_in, t.n_post = L.n_in.data_ptr(), L.n_post.data_ptr()
+                t.n_preff = L.n_preff.data_ptr() if hasattr(L, "n_preff") else None
+                t.n_postff = L.n_postff.data_ptr() if hasattr(L, "n_postff") else None
+            self._ltab = tab
+        return self._ltab
+
+    def _text_pass_native(self, ids, kv, seg, text_cache, logits_to_keep):
+        """engine.text_pass through the native executor (csrc/textpass.cu): one C call enqueues every layer's kernels -- the same
+        kernels with the same arguments as _TextRun, so the results are bit-identical to the per-layer Python path."""
+        import ctypes as C
+        from . import lib as _lib
+        from .lib import VidiTextPass
+        c = self.cfg.llm
+        gm = self.gemma
+        Tq = ids.numel()
+        d = VidiTextPass()
+        d.Tq, d.pos0, d.layers, d.hidden, d.heads, d.kv_heads, d.head_dim = Tq, 0, c.layers, c.hidden, c.heads, c.kv_heads, c.head_dim
+        d.inter, d.vocab, d.gemma, d.glu = c.inter, c.vocab, int(gm), self.glu
+        d.sliding_window = int(getattr(c, "sliding_window", 0) or 0)
+        d.logits_keep = int(logits_to_keep or 0)
+        d.rms_eps, d.normalizer = c.rms_eps, self.normalizer
+        d.scale = c.query_pre_attn_scalar ** -0.5 if gm else c.head_dim ** -0.5
+        d.attn_softcap = (c.attn_softcap or 0.0) if gm else 0.0
+        d.final_softcap = (c.final_softcap or 0.0) if gm else 0.0
+        d.layer_w = self._layer_table()
+        d.embed, d.final_norm, d.lm_head = self.W.embed.data_ptr(), self.W.final_norm.data_ptr(), self.W.lm_head.data_ptr()
+        d.inv_freq, d.ids = self.W.inv_freq.data_ptr(), ids.data_ptr()
+        assert ids.dtype == torch.int64 and ids.is_contiguous()
+        if text_cache is not None:
+            tkv = text_cache["kv"]
+            d.pos0 = text_cache["len"]
+            assert d.pos0 + Tq <= tkv.shape[1], "text KV cache too small"
+            d.text_kv, d.text_kv_layer_stride, d.text_kv_ld = tkv.data_ptr(), tkv.stride(0), tkv.stride(1)
+        d.stream_kv = kv.data_ptr() if kv.numel() else None
+        d.stream_layer_stride, d.stream_ld = (kv.stride(0), kv.stride(1)) if kv.numel() else (0, 2 * c.kv_dim)
+        d.nseg = len(seg)
+        for i, (r0, nr, kmask, gate, n_total) in enumerate(seg):
+            sg = d.seg[i]
+            sg.row0, sg.rows, sg.gate = r0, nr, gate
+            sg.splits = max(1, ops.xattn_splits(-(-n_total // self.world), c.kv_heads, self.n_sms) + self.split_bias)
+            sg.kmask = kmask.data_ptr() if (kmask is not None and kmask.numel()) else None
+        d.world, d.rank = self.world, self.rank
+        x = self.xchg
+        if self.world > 1:
+            d.seq0, d.cap = x.seq, x.cap
+            for r in range(self.world):
+                d.peer_data[r] = x.arenas[r]
+                d.peer_flags[r] = x.arenas[r] + x.flags_off
+            d.counter, d.err = x.counter_ptr, x.err_ptr
+        L = _lib.load()
+        need = int(L.vidi_text_pass_workspace_bytes(C.byref(d)))
+        ws = getattr(self, "_text_ws", None)
+        if ws is None or ws.numel() < need:
+            ws = self._text_ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        keep = Tq if not logits_to_keep or logits_to_keep >= Tq else logits_to_keep
+        logits = torch.empty(keep, c.vocab, device=self.device, dtype=torch.float32)
+        d.workspace, d.workspace_bytes, d.logits = ws.data_ptr(), ws.numel(), logits.data_ptr()
+        _lib.check(L.vidi_text_pass(C.byref(d), ops._stream()), "text_pass")
+        if self.world > 1:
+            x.seq += c.layers
+        if text_cache is not None:
+            text_cache["len"] = d.pos0 + Tq
+        return logits
 
     # ------------------------------------------------------------------------------------------
     # whole prefill for one sample
@@ -409,7 +490,7 @@ class _TextRun:
         self.rows = self.Tq * c.heads
         dh = c.head_dim
         # one flat fp32 buffer per layer holds every stream's [O | LSE] split partials of this rank
-        self.splits = [ops.xattn_splits(-(-s[4] // eng.world), c.kv_heads, eng.n_sms) for s in seg]
+        self.splits = [max(1, ops.xattn_splits(-(-s[4] // eng.world), c.kv_heads, eng.n_sms) + eng.split_bias) for s in seg]
         self.sizes = [sp * self.rows * (dh + 1) for sp in self.splits]
         self.flat = torch.empty(max(1, sum(self.sizes)), device=eng.device, dtype=torch.float32)
         # multi-rank: each rank first reduces its own splits to ONE (O, LSE) partial per stream (xchg.cu), and only those cross ranks:

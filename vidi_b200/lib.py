@@ -60,7 +60,31 @@ SIGNATURES = {
     "vidi_rope_inplace": [_p, _l, _i, _i, _i, _i, _p, _i, _p],
     "vidi_attn_text": [_p, _l, _p, _p, _l, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p, _p],
 }
-EXTRA_SYMBOLS = ["vidi_last_error", "vidi_abi_version", "vidi_launch_count", "vidi_reset_launch_count"]
+
+
+class VidiTextLayerW(C.Structure):
+    _fields_ = [(n, _p) for n in ("wqkv", "wo", "wgu", "wd", "n_in", "n_post", "n_preff", "n_postff")]
+
+
+class VidiTextSeg(C.Structure):
+    _fields_ = [("row0", _l), ("rows", C.c_int32), ("splits", C.c_int32), ("kmask", _p), ("gate", _f), ("reserved", C.c_int32)]
+
+
+class VidiTextPass(C.Structure):
+    """mirror of ``struct VidiTextPass`` (include/vidi_b200.h); tests/test_host_cpu.py checks the layout against the C compiler"""
+    _fields_ = ([(n, C.c_int32) for n in ("Tq", "pos0", "layers", "hidden", "heads", "kv_heads", "head_dim", "inter", "vocab", "gemma",
+                                          "glu", "sliding_window", "logits_keep")]
+                + [(n, _f) for n in ("rms_eps", "scale", "attn_softcap", "final_softcap", "normalizer")]
+                + [("layer_w", C.POINTER(VidiTextLayerW)), ("embed", _p), ("final_norm", _p), ("lm_head", _p), ("inv_freq", _p), ("ids", _p),
+                   ("text_kv", _p), ("text_kv_layer_stride", _l), ("text_kv_ld", _l),
+                   ("stream_kv", _p), ("stream_layer_stride", _l), ("stream_ld", _l),
+                   ("nseg", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("seq0", C.c_uint32),
+                   ("seg", VidiTextSeg * 2), ("peer_data", _p * 16), ("peer_flags", _p * 16), ("cap", _l),
+                   ("counter", _p), ("err", _p), ("workspace", _p), ("workspace_bytes", _l), ("logits", _p)])
+
+
+SIGNATURES["vidi_text_pass"] = [C.POINTER(VidiTextPass), _p]
+EXTRA_SYMBOLS = ["vidi_last_error", "vidi_abi_version", "vidi_launch_count", "vidi_reset_launch_count", "vidi_text_pass_workspace_bytes"]
 
 _lib = None
 
@@ -83,6 +107,8 @@ def load() -> C.CDLL:
     lib.vidi_abi_version.restype = C.c_int
     lib.vidi_launch_count.restype = C.c_int64
     lib.vidi_reset_launch_count.restype = None
+    lib.vidi_text_pass_workspace_bytes.argtypes = [C.POINTER(VidiTextPass)]
+    lib.vidi_text_pass_workspace_bytes.restype = C.c_int64
     _lib = lib
     return lib
 

@@ -18,7 +18,7 @@ from typing import List, Optional
 
 import torch
 
-from .config import Vidi15Config, LLMCfg, VisionCfg, AudioCfg, vidi15_9b
+from .config import Vidi15Config, Vidi7BConfig, LLMCfg, MistralCfg, VisionCfg, AudioCfg, vidi15_9b
 from .engine import Vidi15Engine, make_plan
 
 IGNORE_INDEX = -100
@@ -38,21 +38,58 @@ class DattnCausalLMOutputWithPast:
 
 
 class StreamKVCache:
-    """Per-layer K,V of an image/audio stream, exposed like the reference's DynamicCache of 3-D
-    ``[B, N, Hkv*dh]`` entries (gemma.py:61-65) but backed by the engine's packed [L, N, 2*kv_dim] buffer."""
+    """Per-layer K,V of an image/audio stream for the whole batch, exposed like the reference's DynamicCache of 3-D
+    ``[B, N, Hkv*dh]`` entries (gemma.py:61-65, 664-670) but backed by the engine's packed per-sample [L, N_b, 2*kv_dim] buffers:
+    ``cache[l]`` -> (K [B, Nmax, kv_dim], V [B, Nmax, kv_dim]), samples right-padded with zeros (views when B == 1)."""
 
-    def __init__(self, kv: torch.Tensor, row0: int, n: int, kv_dim: int):
-        self.kv, self.row0, self.n, self.kv_dim = kv, row0, n, kv_dim
+    def __init__(self, states: list, which: int, kv_dim: int):
+        self.states, self.which, self.kv_dim = states, which, kv_dim
+
+    def _rows(self, b: int, l: int):
+        st = self.states[b]
+        r0, n = st.seg[self.which][0], st.seg[self.which][1]
+        return st.kv[l, r0:r0 + n]
 
     def __len__(self):
-        return self.kv.shape[0]
+        return self.states[0].kv.shape[0]
 
     def __getitem__(self, l):
-        rows = self.kv[l, self.row0:self.row0 + self.n]
-        return rows[None, :, :self.kv_dim], rows[None, :, self.kv_dim:]
+        rows = [self._rows(b, l) for b in range(len(self.states))]
+        if len(rows) == 1:
+            r = rows[0][None]
+        else:
+            n = max(x.shape[0] for x in rows)
+            r = rows[0].new_zeros(len(rows), n, rows[0].shape[1])
+            for b, x in enumerate(rows):
+                r[b, :x.shape[0]] = x
+        return r[:, :, :self.kv_dim], r[:, :, self.kv_dim:]
 
     def get_seq_length(self, layer_idx: int = 0):
-        return self.n
+        return max(st.seg[self.which][1] for st in self.states)
+
+
+class TextKVCache:
+    """The text stream's self-attention cache of every sample (slot ``past_key_values`` of the reference's output, gemma.py:684):
+    ``cache[l]`` -> (K [B, Hkv, T, dh], V [B, Hkv, T, dh]) in the HF layout, RoPE already applied to K as HF stores it."""
+
+    def __init__(self, states: list, kv_heads: int, head_dim: int):
+        self.states, self.kv_heads, self.head_dim = states, kv_heads, head_dim
+
+    def __len__(self):
+        return self.states[0].text_cache["kv"].shape[0]
+
+    def get_seq_length(self, layer_idx: int = 0):
+        return max(st.text_cache["len"] for st in self.states)
+
+    def __getitem__(self, l):
+        T, kd = self.get_seq_length(), self.kv_heads * self.head_dim
+        rows = self.states[0].text_cache["kv"].new_zeros(len(self.states), T, 2 * kd)
+        for b, st in enumerate(self.states):
+            n = st.text_cache["len"]
+            rows[b, :n] = st.text_cache["kv"][l, :n]
+        k = rows[:, :, :kd].reshape(len(self.states), T, self.kv_heads, self.head_dim).transpose(1, 2)
+        v = rows[:, :, kd:].reshape(len(self.states), T, self.kv_heads, self.head_dim).transpose(1, 2)
+        return k, v
 
 
 class _PrefillState:
@@ -60,6 +97,22 @@ class _PrefillState:
 
     def __init__(self, kv, seg, text_cache):
         self.kv, self.seg, self.text_cache = kv, seg, text_cache
+
+
+def hf_like_config(cfg) -> SimpleNamespace:
+    """``model.config`` as the reference's callers read it (plain attribute bag; mm_splits stays settable, inference.py:86)."""
+    c = cfg.llm
+    gemma = hasattr(c, "final_softcap")
+    # eos: 107 for the Gemma2 build (gemma.py:461-462); Mistral keeps the tokenizer's </s> = 2
+    # mm_image_aspect_ratio: read by the reference's process_images(video, image_processor, model.config) (img_utils.py:173-198);
+    # anything but "resize" / "pad" / "anyres" / "crop" raises there -- the checkpoints ship "resize" (Dattn*Config defaults)
+    return SimpleNamespace(mm_splits=cfg.mm_splits, eos_token_id=107 if gemma else 2, pad_token_id=0,
+                           vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers,
+                           mm_image_aspect_ratio=getattr(cfg, "mm_image_aspect_ratio", "resize"),
+                           mm_input_type="video", mm_image_pool_size=cfg.mm_image_pool_size,
+                           mm_audio_pool_size=cfg.mm_audio_pool_size, mm_time_interval=cfg.mm_time_interval,
+                           final_logit_softcapping=getattr(c, "final_softcap", None),
+                           model_type="dattn_gemma2" if gemma else "dattn_mistral")
 
 
 class DattnGemma2ForCausalLM:
@@ -72,15 +125,7 @@ class DattnGemma2ForCausalLM:
         self.cfg = cfg
         self.device = self.engine.device
         self.dtype = BF16
-        c = cfg.llm
-        gemma = hasattr(c, "final_softcap")
-        # eos: 107 for the Gemma2 build (gemma.py:461-462); Mistral keeps the tokenizer's </s> = 2
-        self.config = SimpleNamespace(mm_splits=cfg.mm_splits, eos_token_id=107 if gemma else 2, pad_token_id=0,
-                                      vocab_size=c.vocab, hidden_size=c.hidden, num_hidden_layers=c.layers,
-                                      mm_input_type="video", mm_image_pool_size=cfg.mm_image_pool_size,
-                                      mm_audio_pool_size=cfg.mm_audio_pool_size, mm_time_interval=cfg.mm_time_interval,
-                                      final_logit_softcapping=getattr(c, "final_softcap", None),
-                                      model_type="dattn_gemma2" if gemma else "dattn_mistral")
+        self.config = hf_like_config(cfg)
         self._mm = SimpleNamespace(text_tokenizer=tokenizer, image_processor=image_processor, audio_processor=audio_processor)
         self.training = False
 
@@ -177,28 +222,46 @@ class DattnGemma2ForCausalLM:
         if input_ids.dim() == 1:
             input_ids = input_ids[None]
         B = input_ids.shape[0]
-        outs, states = [], []
-        for b in range(B):
-            ids = self._strip(input_ids[b], attention_mask[b] if attention_mask is not None else None)   # None mask == ones (Q16)
-            img = images[b] if images is not None else None
-            aud = audios[b] if audios is not None else None
-            asz = int(audio_sizes[b]) if audio_sizes is not None else (aud.shape[0] * self.cfg.aud.nb_max_frames if aud is not None else 0)
-            lg, st = self._prefill_one(ids, img, aud, asz, ids.numel() + 1, logits_to_keep, mm_total=kw.get("mm_total"))
-            outs.append(lg); states.append(st)
+        c = self.cfg.llm
+        if isinstance(past_key_values, TextKVCache):
+            # continuation on the engine's caches (what HF's loop does through prepare_inputs_for_generation, gemma.py:657-672):
+            # the new token ids of every sample run the text stream against the three caches of the prefill
+            states = past_key_values.states
+            assert len(states) == B, "past_key_values holds a different batch size"
+            outs = []
+            for b in range(B):
+                ids = self._strip(input_ids[b], None).to(self.device, dtype=torch.int64).contiguous()
+                st = states[b]
+                need = st.text_cache["len"] + ids.numel()
+                if need > st.text_cache["kv"].shape[1]:                  # grow the text cache (prefill sized it for T + 1)
+                    grown = self.engine.new_text_cache(max(need, 2 * st.text_cache["kv"].shape[1]))
+                    grown["kv"][:, :st.text_cache["len"]] = st.text_cache["kv"][:, :st.text_cache["len"]]
+                    grown["len"] = st.text_cache["len"]
+                    st.text_cache = grown
+                outs.append(self.engine.text_pass(ids, st.kv, st.seg, text_cache=st.text_cache, logits_to_keep=logits_to_keep))
+        else:
+            outs, states = [], []
+            for b in range(B):
+                ids = self._strip(input_ids[b], attention_mask[b] if attention_mask is not None else None)   # None mask == ones (Q16)
+                img = images[b] if images is not None else None
+                aud = audios[b] if audios is not None else None
+                asz = int(audio_sizes[b]) if audio_sizes is not None else (aud.shape[0] * self.cfg.aud.nb_max_frames if aud is not None else 0)
+                lg, st = self._prefill_one(ids, img, aud, asz, ids.numel() + 1, logits_to_keep, mm_total=kw.get("mm_total"))
+                outs.append(lg); states.append(st)
         T = max(o.shape[0] for o in outs)
         logits = torch.zeros(B, T, outs[0].shape[1], device=self.device, dtype=torch.float32)
         for b, o in enumerate(outs):
             logits[b, :o.shape[0]] = o                                    # right padding (gemma.py:459 padding_side)
-        kd = self.cfg.llm.kv_dim
-        st0 = states[0]
-        img_c = aud_c = None
-        si = 0
-        if images is not None:
-            r0, n = st0.seg[si][0], st0.seg[si][1]; img_c = StreamKVCache(st0.kv, r0, n, kd); si += 1
-        if audios is not None:
-            r0, n = st0.seg[si][0], st0.seg[si][1]; aud_c = StreamKVCache(st0.kv, r0, n, kd)
-        return DattnCausalLMOutputWithPast(logits=logits, past_key_values=st0.text_cache, past_image_key_values=img_c,
-                                           past_audio_key_values=aud_c)
+        # the three cache slots hold EVERY sample of the batch (gemma.py:664-670, 684-685)
+        kinds = [k for k, present in (("img", images is not None or isinstance(past_image_key_values, StreamKVCache)),
+                                      ("aud", audios is not None or isinstance(past_audio_key_values, StreamKVCache))) if present]
+        if isinstance(past_key_values, TextKVCache):
+            img_c, aud_c = past_image_key_values, past_audio_key_values
+        else:
+            img_c = StreamKVCache(states, kinds.index("img"), c.kv_dim) if "img" in kinds else None
+            aud_c = StreamKVCache(states, kinds.index("aud"), c.kv_dim) if "aud" in kinds else None
+        return DattnCausalLMOutputWithPast(logits=logits, past_key_values=TextKVCache(states, c.kv_heads, c.head_dim),
+                                           past_image_key_values=img_c, past_audio_key_values=aud_c)
 
     # --- generate ----------------------------------------------------------------------------------
     @torch.no_grad()
@@ -250,21 +313,33 @@ class DattnMistralForCausalLM(DattnGemma2ForCausalLM):
 # -------------------------------------------------------------------------------------------------
 # loader (builder.py:24-64)
 # -------------------------------------------------------------------------------------------------
-def config_from_hf_json(cfg_json: dict) -> Vidi15Config:
-    """Build the engine config from a checkpoint's config.json (keys of DattnGemma2Config, gemma.py:427-448)."""
+def config_from_hf_json(cfg_json: dict):
+    """Build the engine config from a checkpoint's config.json: keys of DattnGemma2Config (gemma.py:427-448) or, for
+    ``model_type == "dattn_mistral"`` / a Mistral architecture, DattnMistralConfig (Vidi_7B/model/lmm/dattn/mistral.py:456-477),
+    the dispatch ``get_dattn_cls`` makes on the checkpoint (Vidi_7B/model/builder.py:49)."""
     g = cfg_json.get
-    llm = LLMCfg(hidden=g("hidden_size", 3584), heads=g("num_attention_heads", 16), kv_heads=g("num_key_value_heads", 8),
-                 head_dim=g("head_dim", 256), inter=g("intermediate_size", 14336), layers=g("num_hidden_layers", 42),
-                 vocab=g("vocab_size", 256000), rms_eps=g("rms_norm_eps", 1e-6), rope_theta=g("rope_theta", 10000.0),
-                 query_pre_attn_scalar=g("query_pre_attn_scalar", 256), attn_softcap=g("attn_logit_softcapping", 50.0),
-                 final_softcap=g("final_logit_softcapping", 30.0), sliding_window=g("sliding_window", 4096),
-                 tie_word_embeddings=g("tie_word_embeddings", True))
     # tower dims: the public SigLIP-so400m/14@384 and Whisper-large-v3 configs unless the checkpoint carries overrides
     vis = VisionCfg(**g("vision_config")) if isinstance(g("vision_config"), dict) else VisionCfg()
     aud = AudioCfg(**g("audio_config")) if isinstance(g("audio_config"), dict) else AudioCfg()
-    return Vidi15Config(llm=llm, vis=vis, aud=aud, mm_image_pool_size=g("mm_image_pool_size", 2),
-                        mm_audio_pool_size=g("mm_audio_pool_size", 5), mm_time_interval=g("mm_time_interval", 10000),
-                        mm_std=g("mm_std", 0.028976401314139366), mm_splits=g("mm_splits", 1))
+    archs = " ".join(g("architectures") or [])
+    mm = dict(mm_audio_pool_size=g("mm_audio_pool_size") or 5, mm_time_interval=g("mm_time_interval") or 10000,
+              mm_std=g("mm_std") or 0.028976401314139366, mm_splits=g("mm_splits") or 1)
+    aspect = g("mm_image_aspect_ratio") or "resize"
+    if g("model_type") == "dattn_mistral" or "Mistral" in archs:       # mm_image_aspect_ratio is carried into model.config (img_utils.py:173-198)
+        hidden, heads = g("hidden_size", 4096), g("num_attention_heads", 32)
+        llm = MistralCfg(hidden=hidden, heads=heads, kv_heads=g("num_key_value_heads", 8), head_dim=g("head_dim") or hidden // heads,
+                         inter=g("intermediate_size", 14336), layers=g("num_hidden_layers", 32), vocab=g("vocab_size", 32000),
+                         rms_eps=g("rms_norm_eps", 1e-5), rope_theta=g("rope_theta", 10000.0),
+                         tie_word_embeddings=g("tie_word_embeddings", False), sliding_window=g("sliding_window") or 0)
+        return Vidi7BConfig(llm=llm, vis=vis, aud=aud, mm_image_pool_size=g("mm_image_pool_size") or 16, mm_image_aspect_ratio=aspect, **mm)
+    else:
+        llm = LLMCfg(hidden=g("hidden_size", 3584), heads=g("num_attention_heads", 16), kv_heads=g("num_key_value_heads", 8),
+                     head_dim=g("head_dim", 256), inter=g("intermediate_size", 14336), layers=g("num_hidden_layers", 42),
+                     vocab=g("vocab_size", 256000), rms_eps=g("rms_norm_eps", 1e-6), rope_theta=g("rope_theta", 10000.0),
+                     query_pre_attn_scalar=g("query_pre_attn_scalar", 256), attn_softcap=g("attn_logit_softcapping", 50.0),
+                     final_softcap=g("final_logit_softcapping", 30.0), sliding_window=g("sliding_window", 4096),
+                     tie_word_embeddings=g("tie_word_embeddings", True))
+    return Vidi15Config(llm=llm, vis=vis, aud=aud, mm_image_pool_size=g("mm_image_pool_size") or 2, mm_image_aspect_ratio=aspect, **mm)
 
 
 def _load_safetensors_dir(path: str) -> dict:
@@ -299,6 +374,9 @@ def load_pretrained_model(model_name_or_path, load_8bit=False, load_4bit=False, 
     from .preprocess import SiglipImageProcessorLite, WhisperFeatureExtractorLite
     image_processor = SiglipImageProcessorLite(cfg.vis.image)
     audio_processor = WhisperFeatureExtractorLite(cfg.aud.mels)
-    model = DattnGemma2ForCausalLM(cfg, sd, device=device, tokenizer=tokenizer, image_processor=image_processor,
-                                   audio_processor=audio_processor, pop_state_dict=True)
+    cls = DattnMistralForCausalLM if isinstance(cfg, Vidi7BConfig) else DattnGemma2ForCausalLM      # get_dattn_cls (builder.py:49)
+    if isinstance(cfg, Vidi7BConfig) and tokenizer is not None and getattr(tokenizer, "pad_token", None) is None:
+        tokenizer.pad_token = tokenizer.unk_token                       # DattnMistralMMModel.build_text_tokenizer (mistral.py:487-493)
+    model = cls(cfg, sd, device=device, tokenizer=tokenizer, image_processor=image_processor, audio_processor=audio_processor,
+                pop_state_dict=True)
     return model, tokenizer, image_processor, audio_processor

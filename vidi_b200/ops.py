@@ -16,6 +16,10 @@ BF16 = torch.bfloat16
 # CTA-pair (cta_group::2) GEMM for large-M problems; flipped on once it beats the 1-CTA kernel on the box
 USE_2CTA = True
 
+# tower attention: exponentiate every ATTN_POLY-th score pair with the FMA-pipe polynomial instead of MUFU.EX2 (0 = MUFU only);
+# validated on B200 in round 2 (tests/test_preprocess_gpu.py::test_attn_dense_poly_exp2_variants), default chosen by measurement
+ATTN_POLY = 0
+
 # bench instrumentation: when PROFILE is a list, every gemm() appends (tag, algorithmic_flops, start_evt, end_evt)
 PROFILE = None
 
@@ -43,8 +47,10 @@ def pick_block_n(M: int, N: int, glu: bool = False) -> int:
         return 256
     if M <= 256 and N <= 16384:
         return 64                       # text stream (M ~ 32): weight-bandwidth bound, spread the N tiles over more SMs
-    if N % 256 != 0 and N % 192 == 0 and N < 2048:
-        return 192                      # 1152, 3456: exact tiling instead of a half-empty last 256 tile
+    if N % 256 != 0 and N % 192 == 0 and N < 2048 and not (USE_2CTA and M >= 1024):
+        return 192                      # 1-CTA kernel, N = 1152: exact tiling instead of a half-empty last 256 tile.  On the CTA-pair
+                                        # kernel (M >= 1024) the 256-wide tile wins despite the padding: sustained tower block, N = 1152
+                                        # sites 832 -> 874 / 1027 -> 1071 TF/s (profiles/r02_tower_ab.txt)
     if N >= 1024 or N % 256 == 0:
         return 256
     return 128 if N > 64 else 64
@@ -302,6 +308,8 @@ def attn_dense(qkv, B: int, S: int, H: int, dh: int, scale: float, out=None, imp
     assert qkv.dtype == BF16 and qkv.shape == (B * S, 3 * d)
     if out is None:
         out = torch.empty(B * S, d, device=qkv.device, dtype=BF16)
+    if impl == "auto" and ATTN_POLY and dh in (64, 72) and S > 128:
+        impl = f"poly{ATTN_POLY}"
     if impl.startswith("poly"):          # A/B only: FMA-pipe exp2 for every (2|3|4)-th score pair, e.g. impl="poly4"
         _lib.check(L.vidi_attn_dense_poly(_ptr(qkv), _rowmajor(qkv), _ptr(out), _rowmajor(out), B, S, H, dh, scale, int(impl[4:]),
                                           _stream()), "attn_dense_poly")

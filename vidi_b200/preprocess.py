@@ -110,6 +110,11 @@ class SiglipImageProcessorLite:
             return {"pixel_values": torch.cat(out, 0)}
         assert frames_uint8.dtype == torch.uint8 and frames_uint8.dim() == 4 and frames_uint8.shape[-1] == 3
         s = self.output_size
+        if frames_uint8.is_cuda:
+            # device path (csrc/preproc.cu): Pillow's two 8-bit passes as kernels, the second fused with the affine and the CHW layout
+            # change; output is bf16 (what the engine consumes; bit-equal to this method's CPU result rounded to bf16)
+            from . import ops
+            return ops.resize_frames_u8(frames_uint8.contiguous(), s, self.rescale_factor, self.image_mean[0], self.image_std[0])
         outs = []
         for i in range(0, frames_uint8.shape[0], chunk):
             r = resize_bicubic_u8(frames_uint8[i:i + chunk], s, s)
@@ -195,6 +200,10 @@ class WhisperFeatureExtractorLite:
         C = max(1, -(-n // self.n_samples))
         buf = torch.zeros(C * self.n_samples, dtype=torch.float32, device=audio.device)
         buf[:n] = audio.to(torch.float32)
+        if audio.is_cuda:
+            # device path (csrc/preproc.cu + two split-bf16 tensor-core GEMMs): bf16 features, <= 1e-3 from the fp64 STFT below
+            from . import ops
+            return ops.log_mel(buf.view(C, self.n_samples), self.feature_size), self.audio_size(n)
         return self.log_mel(buf.view(C, self.n_samples)), self.audio_size(n)
 
 
