@@ -284,6 +284,8 @@ def run_ours(args):
     eng = model.engine
     if args.no_overlap:
         eng.overlap_text = False
+    if args.llm_cta2 is not None:
+        eng.llm_cta2 = bool(args.llm_cta2)
     if args.ln_fold:
         eng.enable_ln_fold(True)
     if args.attn_poly is not None:
@@ -414,6 +416,36 @@ def run_ours(args):
         barrier()
         text_ms = round(a_.elapsed_time(b_) / 3, 2)
         del st_
+    # decode: q_len = 1 greedy steps on the caches of a prefill, through the same engine.text_pass (native executor);
+    # per token the GPU streams the text GEMM weights + lm_head once and this rank's shard of the image/audio K||V cache once
+    decode = None
+    if not args.quick and clips == 1:
+        tc = eng.new_text_cache(T + 64)
+        lg, st_ = eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, return_state=True, text_cache=tc, logits_to_keep=1)
+        nxt = lg[-1].argmax().reshape(1)
+        for _ in range(3):
+            lg = eng.text_pass(nxt, st_["kv"], st_["seg"], text_cache=tc, logits_to_keep=1); nxt = lg[-1].argmax().reshape(1)
+        barrier()
+        n_dec = 16
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host = 0.0
+        a_.record()
+        for _ in range(n_dec):
+            h0 = time.perf_counter()
+            lg = eng.text_pass(nxt, st_["kv"], st_["seg"], text_cache=tc, logits_to_keep=1)
+            t_host += time.perf_counter() - h0
+            nxt = lg[-1].argmax().reshape(1)                     # stays on the device: no host sync inside the loop
+        b_.record()
+        barrier()
+        ms_tok = a_.elapsed_time(b_) / n_dec
+        c_ = cfg.llm
+        w_bytes = c_.layers * 2 * (c_.hidden * (c_.q_dim + 2 * c_.kv_dim) + c_.q_dim * c_.hidden + 3 * c_.hidden * c_.inter) + 2 * c_.vocab * c_.hidden
+        kv_bytes = c_.layers * (plan.n_img + plan.n_aud) * 2 * c_.kv_dim * 2
+        decode = dict(tokens_per_s=round(1e3 / ms_tok, 1), ms_per_token=round(ms_tok, 3), host_enqueue_ms_per_token=round(t_host / n_dec * 1e3, 3),
+                      steps=n_dec, context_tokens=n_tokens, bytes_per_token=int(w_bytes + kv_bytes), weight_bytes=int(w_bytes), kv_bytes_this_rank=int(kv_bytes),
+                      hbm_gbs=round((w_bytes + kv_bytes) / ms_tok / 1e6, 1), hbm_frac=round((w_bytes + kv_bytes) / ms_tok / 1e6 / pk["hbm"], 4),
+                      note="greedy q_len=1 steps against the prefill's caches (text K||V + this rank's image/audio K||V shard); argmax stays on the device")
+        del st_, tc
     # end-to-end through the public API with host buffers
     if args.quick:
         ms_e2e = ms
@@ -454,8 +486,9 @@ def run_ours(args):
                               "outside this region too); mm_total=(F, C) tells the facade that each rank was handed only its own shard of frames / chunks"),
                 other_ops_ms_per_step={k: v[0] for k, v in sorted(getattr(timed, "by_op", {}).items(), key=lambda kv: -kv[1][0])},
                 gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
-                text_pass_ms=text_ms, logits_digest=digest, multi_gpu_parity=parity, exchange=eng.exchange_note,
-                gemm_variant="2cta (cta_group::2) on tower/projector sites with M>=1024, 1cta on stream-pass and text sites" if ops.USE_2CTA else "1cta")
+                text_pass_ms=text_ms, decode=decode, logits_digest=digest, multi_gpu_parity=parity, exchange=eng.exchange_note,
+                gemm_variant=(("2cta (cta_group::2) on tower/projector" + (" and stream-pass" if eng.llm_cta2 else "") + " sites with M>=1024, 1cta on "
+                              + ("" if eng.llm_cta2 else "stream-pass and ") + "text sites") if ops.USE_2CTA else "1cta"))
     print(json.dumps(line), flush=True)
 
 
@@ -469,6 +502,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm", default="auto", choices=["auto", "1cta", "2cta"], help="A/B switch for the CTA-pair GEMM")
     ap.add_argument("--no-overlap", action="store_true", help="A/B: run the text pass after the stream pass instead of on the side stream")
+    ap.add_argument("--llm-cta2", type=int, default=None, help="A/B: CTA-pair GEMM on the stream-pass sites too (1) or not (0)")
     ap.add_argument("--ln-fold", action="store_true", help="A/B: LayerNorm folded into the tower GEMMs (engine.enable_ln_fold)")
     ap.add_argument("--attn-poly", type=int, default=None, help="A/B: tower attention with every n-th score pair on the FMA-pipe exp2 (0 = off)")
     ap.add_argument("--quick", action="store_true", help="1 warm-up, no e2e / cpu legs (for ncu launch lists; not a bench value)")

@@ -138,6 +138,13 @@ int vidi_attn_dense_mma(const void* qkv, int64_t ld, int q_off, int k_off, int v
 int vidi_xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
                        int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
                        void* stream);
+/* Both key segments of a layer (image rows and audio rows of the same K||V cache: the T2V and T2A calls of gemma.py:185-192 and
+ * 206-221) in one call; on the tcgen05 path ONE launch whose grid covers the key splits of both segments.  K / V point at cache row 0
+ * of the layer (n_rows_total rows); segment i = rows [row0[i], row0[i]+rows[i]) in splits[i] key ranges with mask masks[i] (or NULL).
+ * Opart fp32 [splits[0]+splits[1]][T][Hq][dh], LSE fp32 [splits[0]+splits[1]][T][Hq] -- segment 1's partials follow segment 0's. */
+int vidi_xattn_splitkv_seg(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int n_rows_total, int nseg,
+                           const int32_t* row0, const int32_t* rows, const int32_t* splits, const uint8_t* const* masks, int T, int Hq,
+                           int Hkv, int dh, float scale, float softcap, float* Opart, float* LSE, void* stream);
 /* same contract, always the warp-level mma.sync kernel (any head dim in {128,256}, soft-cap optional: the Vidi-7B path) */
 int vidi_xattn_splitkv_mma(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T,
                            int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
@@ -226,8 +233,10 @@ typedef struct VidiTextPass {
     const void* stream_kv;   /* bf16 [layers][N][2*kv_dim] image+audio K||V cache of this rank */
     int64_t stream_layer_stride, stream_ld;      /* in elements */
     int32_t nseg;
+    int32_t stream_rows;     /* rows N of the stream K||V cache (per layer) */
     int32_t world, rank;     /* world > 1: partials cross ranks through the peer arenas below (see vidi_xattn_premerge_push) */
     uint32_t seq0;           /* sequence number of the last exchange issued before this call; layer l uses seq0 + l + 1     */
+    int32_t reserved0;
     VidiTextSeg seg[2];
     float* peer_data[16];    /* arena data base of every rank (peer-mapped): fp32 [2 slots][world][cap]                      */
     uint32_t* peer_flags[16];/* arena flag base of every rank: uint32 [2 slots][world]                                      */

@@ -190,3 +190,32 @@ def test_vidi7b_loader_generate_and_ask(tmp_path):
     ip, ap = SiglipImageProcessorLite(cfg.vis.image), WhisperFeatureExtractorLite(cfg.aud.mels)
     out = P.ask("a dog running.", frames.cuda(), audio.cuda(), length, model, tok, ip, ap, family="vidi7b", max_new_tokens=16)
     assert out == "00:06:40-00:16:40"
+
+
+def test_vue_runner_on_engine_encodes_each_video_once():
+    """vue_runner.run_queries on the real engine: two queries on one video and one on another; every record carries the chain fixture's
+    answer scaled by its duration; the towers + stream pass run once per video (launch counter), every query only the text stream."""
+    from vidi_b200 import ops, vue_runner as V
+    from vidi_b200.preprocess import SiglipImageProcessorLite, WhisperFeatureExtractorLite
+    cfg, sd, tok, ids, model = _fixture()
+    g = torch.Generator().manual_seed(9)
+    vids = {v: (torch.randint(0, 256, (3 + i, 90, 160, 3), generator=g, dtype=torch.uint8).cuda(), (0.1 * torch.randn(16000 * 4, generator=g)).cuda())
+            for i, v in enumerate(("vA", "vB"))}
+    qs = [dict(query_id=1, video_id="vA", duration=4000.0, query="a dog running."),
+          dict(query_id=2, video_id="vB", duration=200.0, query="somebody opens a door"),
+          dict(query_id=5, video_id="vA", duration=4000.0, query="a red car")]
+    ip, ap = SiglipImageProcessorLite(cfg.vis.image), WhisperFeatureExtractorLite(cfg.aud.mels)
+    encodes = []
+    orig = model.encode_media
+    model.encode_media = lambda *a, **k: (encodes.append(1), orig(*a, **k))[1]
+    recs = V.run_queries(qs, lambda v: vids[v], model, tok, ip, ap, max_new_tokens=40)
+    assert len(encodes) == 2
+    assert [r["query_id"] for r in recs] == [1, 2, 5]
+    assert recs[0]["answer"] == recs[2]["answer"] == [[0.10 * 4000.0, 0.25 * 4000.0], [0.50 * 4000.0, 0.75 * 4000.0]]
+    assert recs[1]["answer"] == [[0.10 * 200.0, 0.25 * 200.0], [0.50 * 200.0, 0.75 * 200.0]]
+    # same answer as the one-shot path (generate with images / audios)
+    video = ip.preprocess(vids["vB"][0]); feats, asz = ap(vids["vB"][1])
+    from vidi_b200 import pipeline as P
+    one = model.generate(P.build_input_ids(qs[1]["query"], tok, "vidi15"), images=video[None], audios=feats[None], audio_sizes=[asz],
+                         do_sample=False, max_new_tokens=40)
+    assert tok.batch_decode(one)[0] == CF.ANSWER

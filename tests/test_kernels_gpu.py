@@ -514,3 +514,74 @@ def test_peer_exchange_missing_peer_sets_error_flag():
     torch.cuda.synchronize()
     with pytest.raises(RuntimeError, match="never delivered"):
         xs[0].check()
+
+
+@pytest.mark.parametrize("dh,cap,G", [(256, 50.0, 2), (128, 0.0, 4)])
+def test_xattn_splitkv_seg_equals_per_segment_launches(dh, cap, G):
+    """One call / one launch over both key segments of a K||V cache (image rows | audio rows, the second with a key mask and a ragged
+    end) must reproduce the per-segment launches bit for bit: same split sizes, same tiles, only the grid is shared.  dh=256 + soft-cap
+    takes the tcgen05 kernel, dh=128 un-capped (Vidi-7B) the warp-level one."""
+    from vidi_b200 import ops
+    T, Hkv = 9, 2
+    Hq = Hkv * G
+    n0, n1 = 1500, 700
+    kv = rnd(n0 + n1 + 37, 2 * Hkv * dh, seed=5).to(BF)             # rows after the segments must be ignored
+    q = rnd(T, Hq * dh, seed=6).to(BF)
+    mask1 = (torch.rand(n1, device="cuda") > 0.3).to(torch.uint8)
+    kd = Hkv * dh
+    splits = [3, 2]
+    rows = T * Hq
+    O = torch.full((sum(splits) * rows * dh,), float("nan"), device="cuda"); Ls = torch.full((sum(splits) * rows,), float("nan"), device="cuda")
+    ops.xattn_splitkv_seg(q, kv[:, :kd], kv[:, kd:], [(0, n0, None), (n0, n1, mask1)], splits, Hq, Hkv, dh, dh ** -0.5, cap, O, Ls)
+    o0, l0 = ops.xattn_splitkv(q, kv[:n0, :kd], kv[:n0, kd:], None, Hq, Hkv, dh, dh ** -0.5, cap, splits[0])
+    o1, l1 = ops.xattn_splitkv(q, kv[n0:n0 + n1, :kd], kv[n0:n0 + n1, kd:], mask1, Hq, Hkv, dh, dh ** -0.5, cap, splits[1])
+    assert torch.equal(O[:splits[0] * rows * dh], o0.reshape(-1)) and torch.equal(O[splits[0] * rows * dh:], o1.reshape(-1))
+    assert torch.equal(Ls[:splits[0] * rows], l0.reshape(-1)) and torch.equal(Ls[splits[0] * rows:], l1.reshape(-1))
+    # and the merged result against fp32 softmax over segment 1 alone (mask applied)
+    out = torch.zeros(rows, dh, device="cuda")
+    ops.xattn_merge(O[splits[0] * rows * dh:].view(splits[1], rows, dh), Ls[splits[0] * rows:].view(splits[1], rows), out)
+    qf = q.float().view(T, Hq, dh); kf = kv[n0:n0 + n1, :kd].float().view(n1, Hkv, dh).repeat_interleave(G, 1)
+    vf = kv[n0:n0 + n1, kd:].float().view(n1, Hkv, dh).repeat_interleave(G, 1)
+    s_ = torch.einsum("thd,nhd->thn", qf, kf) * dh ** -0.5
+    if cap > 0:
+        s_ = cap * torch.tanh(s_ / cap)
+    s_ = s_.masked_fill(mask1[None, None, :] == 0, float("-inf"))
+    ref = torch.einsum("thn,nhd->thd", torch.softmax(s_, -1), vf).reshape(rows, dh)
+    assert rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("case", ["late_spike", "masked_first_tile_then_very_negative", "benign"])
+def test_xattn_uncapped_dh128_tcgen05_reference_window(case):
+    """Vidi-7B cross attention (dh = 128, no soft-cap, Vidi_7B xattn.py:99-175) on the tcgen05 kernel: the per-row softmax reference is
+    fixed after the first key tile.  'late_spike' puts logits ~180 nats above the first tile's max in a later tile and
+    'masked_first_tile_then_very_negative' leaves the first tile without a valid key and all later logits ~ -150: both must take the
+    in-kernel second pass and still match fp32 softmax and the warp-level kernel."""
+    from vidi_b200 import ops
+    T, Hkv, G, dh, N = 5, 2, 4, 128, 640
+    Hq = Hkv * G
+    q = rnd(T, Hq * dh, seed=11).to(BF)
+    kv = rnd(N, 2 * Hkv * dh, seed=12).to(BF)
+    kd = Hkv * dh
+    mask = torch.ones(N, device="cuda", dtype=torch.uint8)
+    scale = dh ** -0.5
+    if case == "late_spike":
+        # keys 300..303 are aligned with the queries of head 0 / token 0 and scaled up: logits ~ +180
+        kv[300:304, :dh] = (q[0, :dh].float() * 14.0).to(BF)
+    elif case == "masked_first_tile_then_very_negative":
+        mask[:64] = 0
+        kv[:, :kd] = (-q[0, :dh].float().repeat(Hkv) * 12.0).to(BF)[None, :]        # every key anti-aligned with token 0 / head 0
+    out = {}
+    for impl in ("auto", "mma"):
+        o, l = ops.xattn_splitkv(q, kv[:, :kd], kv[:, kd:], mask, Hq, Hkv, dh, scale, 0.0, 2, impl=impl)
+        m = torch.zeros(T * Hq, dh, device="cuda")
+        ops.xattn_merge(o, l, m)
+        out[impl] = m
+    qf = q.float().view(T, Hq, dh); kf = kv[:, :kd].float().view(N, Hkv, dh).repeat_interleave(G, 1)
+    vf = kv[:, kd:].float().view(N, Hkv, dh).repeat_interleave(G, 1)
+    s_ = (torch.einsum("thd,nhd->thn", qf, kf) * scale).masked_fill(mask[None, None, :] == 0, float("-inf"))
+    ref = torch.einsum("thn,nhd->thd", torch.softmax(s_, -1), vf).reshape(T * Hq, dh)
+    if case != "benign":
+        assert float(s_[torch.isfinite(s_)].abs().max()) > 100.0          # the case really leaves the +-100 (log2) window
+    assert torch.isfinite(out["auto"]).all()
+    assert rel_err(out["auto"], ref) < 1e-2, rel_err(out["auto"], ref)
+    assert rel_err(out["mma"], ref) < 1e-2

@@ -69,3 +69,44 @@ def test_ask_plumbing_with_stub_model():
     from vidi_b200.postprocess import format_time_ranges
     assert format_time_ranges(answer, 4000.0) == "00:06:40-00:16:40, 00:33:20-00:50:00"
     assert isinstance(out, str)
+
+
+def test_vue_runner_schema_grouping_and_scorer_join(tmp_path):
+    """Batched VUE-TR-V2 runner (vue_runner.py): result records in the README.md:78-95 schema, one media encode per VIDEO (not per query),
+    and the records survive the join qa_eval.py::load_result performs (query_id join, floor / ceil of the predicted ranges)."""
+    from vidi_b200 import vue_runner as V
+    tok = FakeTokenizer("gemma2")
+
+    class Stub:
+        def __init__(self):
+            self.encodes, self.generates = 0, 0
+
+        def encode_media(self, video, feats, audio_size):
+            self.encodes += 1
+            return ("media", video.shape[0], audio_size)
+
+        def generate(self, ids, media=None, **kw):
+            self.generates += 1
+            assert media[0] == "media" and kw["do_sample"] is False and int((ids == -200).sum()) == 1
+            return torch.tensor([[1, 2, 3]])
+
+    tok.batch_decode = lambda ids, skip_special_tokens=True: ["0.10-0.25, 0.5-0.75"]
+    model = Stub()
+    gts = [dict(query_id=7, video_id="vA", duration=4000.0, query="a dog.", gt=[[405, 990]], task="temporal_retrieval"),
+           dict(query_id=3, video_id="vB", duration=100.0, query="a cat", gt=[[0, 10]], task="temporal_retrieval"),
+           dict(query_id=9, video_id="vA", duration=4000.0, query="two dogs", gt=[[2000, 3000]], task="temporal_retrieval")]
+    g = torch.Generator().manual_seed(0)
+
+    def media(vid):
+        return torch.randint(0, 256, (3, 36, 64, 3), generator=g, dtype=torch.uint8), 0.1 * torch.randn(16000 * 3, generator=g)
+    recs = V.run_queries(gts, media, model, tok, SiglipImageProcessorLite(32), WhisperFeatureExtractorLite(128))
+    assert model.encodes == 2 and model.generates == 3                      # vA encoded once for its two queries
+    assert [r["query_id"] for r in recs] == [7, 3, 9]
+    assert set(recs[0]) == {"query_id", "video_id", "duration", "query", "answer", "task"}
+    assert recs[0]["answer"] == [[400.0, 1000.0], [2000.0, 3000.0]] and recs[1]["answer"] == [[10.0, 25.0], [50.0, 75.0]]
+    path = tmp_path / "results_vidi_b200.json"
+    V.write_results(str(path), recs)
+    rows = V.merge_with_ground_truth(gts, json.load(open(path)))
+    assert rows[0]["gt"] == [[405, 990]] and rows[0]["answer"][0] == [400, 1000]
+    assert abs(V.temporal_iou(rows[0]["answer"][:1], rows[0]["gt"]) - 585 / 600) < 1e-9
+    assert V.temporal_iou(rows[2]["answer"][1:], rows[2]["gt"]) == 1.0

@@ -597,11 +597,7 @@ template <int DH, int DHP>
 static int launch_dense(const void* qkv, int64_t ld, int q_off, int k_off, int v_off, void* out, int64_t ldo, int B, int S,
                         int H, float scale, cudaStream_t st) {
     using Cfg = DenseCfg<DH, DHP>;
-    static bool attr = false;
-    if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_dense_kernel<DH, DHP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr = true;
-    }
+    VB_SET_SMEM_ONCE(Cfg::kSmem, attn_dense_kernel<DH, DHP>);
     dim3 grid((S + Cfg::BM - 1) / Cfg::BM, H, B);
     attn_dense_kernel<DH, DHP><<<grid, 128, Cfg::kSmem, st>>>((const __nv_bfloat16*)qkv, ld, q_off, k_off, v_off,
                                                               (__nv_bfloat16*)out, ldo, S, H, scale * kLog2e);
@@ -624,11 +620,7 @@ static int launch_xattn(const void* Q, int64_t ldq, const void* K, const void* V
                         int N, int Hq, int Hkv, int splits, int keys_per_split, float scale, float softcap, float* Opart,
                         float* LSE, cudaStream_t st) {
     using Cfg = XCfg<DH>;
-    static bool attr = false;
-    if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(xattn_splitkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr = true;
-    }
+    VB_SET_SMEM_ONCE(Cfg::kSmem, xattn_splitkv_kernel<DH>);
     const int G = Hq / Hkv;
     dim3 grid(splits, Hkv, (T * G + Cfg::BM - 1) / Cfg::BM);
     xattn_splitkv_kernel<DH><<<grid, 128, Cfg::kSmem, st>>>((const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)K,
@@ -640,6 +632,7 @@ static int launch_xattn(const void* Q, int64_t ldq, const void* K, const void* V
 
 int xattn_splitkv_sm100(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int,
                         float, float, float*, float*, cudaStream_t);
+bool xattn_sm100_supports(int dh, float softcap);
 
 int xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, const uint8_t* kmask, int T, int N,
                   int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE, int force_mma,
@@ -649,15 +642,50 @@ int xattn_splitkv(const void* Q, int64_t ldq, const void* K, const void* V, int6
     int kps = (N + splits - 1) / splits;
     kps = ((kps + 63) / 64) * 64;
     if (kps == 0) kps = 64;
-    // soft-capped dh=256 (Gemma2) -> tcgen05/TMEM/TMA streaming kernel; otherwise the warp-level mma.sync kernel
+    // soft-capped dh=256 (Gemma2) and un-capped dh=128 (Mistral) -> tcgen05/TMEM/TMA streaming kernel; otherwise the warp-level kernel
     const int G = Hq / Hkv;
-    if (!force_mma && dh == 256 && softcap > 0.f && softcap * kLog2e <= 80.f && 128 % G == 0 &&
+    if (!force_mma && xattn_sm100_supports(dh, softcap) && 128 % G == 0 &&
         (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (kmask == nullptr || (reinterpret_cast<uintptr_t>(kmask) & 15) == 0))
-        return xattn_splitkv_sm100(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
+        return xattn_splitkv_sm100(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, st);
     if (dh == 256) return launch_xattn<256>(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
     if (dh == 128) return launch_xattn<128>(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, splits, kps, scale, softcap, Opart, LSE, st);
     VB_REQUIRE(false, "xattn_splitkv: unsupported head_dim %d (have 128, 256)", dh);
+}
+
+int xattn_splitkv_sm100_seg(const void*, int64_t, const void*, const void*, int64_t, int, int, const int*, const int*, const int*,
+                            const uint8_t* const*, int, int, int, int, float, float, float*, float*, cudaStream_t);
+
+// Both streams of a layer (image rows, audio rows of the same K||V cache) in one call -- and, on the tcgen05 path, ONE launch whose
+// grid covers the splits of both segments (no second prologue / tail per layer).  K / V point at cache row 0 of the layer.
+// Opart [splits[0] + splits[1]][T][Hq][dh], LSE [splits[0] + splits[1]][T][Hq]; segment 1's partials follow segment 0's.
+int xattn_splitkv_seg(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int n_rows_total, int nseg, const int* row0,
+                      const int* rows, const int* splits, const uint8_t* const* masks, int T, int Hq, int Hkv, int dh, float scale,
+                      float softcap, float* Opart, float* LSE, int force_mma, int* launches, cudaStream_t st) {
+    VB_REQUIRE(T > 0 && nseg >= 1 && nseg <= 2 && Hq % Hkv == 0, "xattn_splitkv_seg: bad shape T=%d nseg=%d", T, nseg);
+    VB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0, "xattn_splitkv_seg: alignment");
+    const int G = Hq / Hkv;
+    bool fast = !force_mma && xattn_sm100_supports(dh, softcap) && 128 % G == 0 &&
+                (reinterpret_cast<uintptr_t>(Q) & 15) == 0 && (reinterpret_cast<uintptr_t>(K) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(V) & 15) == 0;
+    for (int i = 0; i < nseg; ++i)
+        if (masks && masks[i] && (reinterpret_cast<uintptr_t>(masks[i]) & 15) != 0) fast = false;
+    if (fast) {
+        if (launches) *launches = 1;
+        return xattn_splitkv_sm100_seg(Q, ldq, K, V, ldkv, n_rows_total, nseg, row0, rows, splits, masks, T, Hq, Hkv, dh, scale, softcap,
+                                       Opart, LSE, st);
+    }
+    int64_t po = 0;
+    for (int i = 0; i < nseg; ++i) {        // warp-level kernel: one launch per segment, same output layout
+        const __nv_bfloat16* kk = reinterpret_cast<const __nv_bfloat16*>(K) + (int64_t)row0[i] * ldkv;
+        const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(V) + (int64_t)row0[i] * ldkv;
+        int rc = xattn_splitkv(Q, ldq, kk, vv, ldkv, masks ? masks[i] : nullptr, T, rows[i], Hq, Hkv, dh, splits[i], scale, softcap,
+                               Opart + po * T * Hq * dh, LSE + po * T * Hq, 1, st);
+        if (rc) return rc;
+        po += splits[i];
+    }
+    if (launches) *launches = nseg;
+    return 0;
 }
 
 int xattn_merge(const float* Opart, const float* LSE, int P, int spr, int64_t rank_stride_o, int64_t rank_stride_l, int rows,

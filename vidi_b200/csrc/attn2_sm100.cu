@@ -380,11 +380,7 @@ static int launch_fa2(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
     } else {
         tm_tail = tm_main;
     }
-    static bool attr = false;
-    if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd2_sm100_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-        attr = true;
-    }
+    VB_SET_SMEM_ONCE(C::kSmem, attn_fwd2_sm100_kernel<DH>);
     Fa2Params p;
     p.S = S; p.H = H; p.B = B;
     p.npair = (S + 2 * C::BM - 1) / (2 * C::BM);

@@ -434,11 +434,7 @@ static int launch_fa3(const void* qkv, int64_t ld, void* out, int64_t ldo, int B
         tm_q_tail = tm_q_main;
         tm_k_tail = tm_k_main;
     }
-    static bool attr = false;
-    if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd3_sm100_kernel<DH, kPolyMod>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-        attr = true;
-    }
+    VB_SET_SMEM_ONCE(C::kSmem, attn_fwd3_sm100_kernel<DH, kPolyMod>);
     Fa3Params p;
     p.S = S; p.H = H; p.B = B;
     p.npair = (S + 2 * C::BM - 1) / (2 * C::BM);

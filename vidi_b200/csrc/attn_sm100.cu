@@ -351,11 +351,7 @@ static int launch_fa(const void* qkv, int64_t ld, void* out, int64_t ldo, int B,
     } else {
         tm_tail = tm_main;
     }
-    static bool attr = false;
-    if (!attr) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_sm100_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-        attr = true;
-    }
+    VB_SET_SMEM_ONCE(C::kSmem, attn_fwd_sm100_kernel<DH>);
     FaParams p;
     p.S = S; p.H = H; p.B = B;
     p.nqb = (S + C::BM - 1) / C::BM;

@@ -42,6 +42,8 @@ int attn_dense_sm100_v3(const void*, int64_t, void*, int64_t, int, int, int, int
 int attn_dense_sm100_v3_poly(const void*, int64_t, void*, int64_t, int, int, int, int, float, int, cudaStream_t);
 int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int, float,
                   float, float*, float*, int, cudaStream_t);
+int xattn_splitkv_seg(const void*, int64_t, const void*, const void*, int64_t, int, int, const int*, const int*, const int*,
+                      const uint8_t* const*, int, int, int, int, float, float, float*, float*, int, int*, cudaStream_t);
 int xattn_merge(const float*, const float*, int, int, int64_t, int64_t, int, int, float, int, float*, cudaStream_t);
 int rope_inplace(void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int text_qk_prep(const void*, int64_t, void*, int64_t, void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
@@ -194,6 +196,15 @@ int vidi_xattn_splitkv_mma(const void* Q, int64_t ldq, const void* K, const void
                            int N, int Hq, int Hkv, int dh, int splits, float scale, float softcap, float* Opart, float* LSE,
                            void* stream) {
     return COUNT(vb::xattn_splitkv(Q, ldq, K, V, ldkv, kmask, T, N, Hq, Hkv, dh, splits, scale, softcap, Opart, LSE, 1, ST(stream)));
+}
+int vidi_xattn_splitkv_seg(const void* Q, int64_t ldq, const void* K, const void* V, int64_t ldkv, int n_rows_total, int nseg,
+                           const int32_t* row0, const int32_t* rows, const int32_t* splits, const uint8_t* const* masks, int T, int Hq,
+                           int Hkv, int dh, float scale, float softcap, float* Opart, float* LSE, void* stream) {
+    int n = 1;
+    const int rc = vb::xattn_splitkv_seg(Q, ldq, K, V, ldkv, n_rows_total, nseg, row0, rows, splits, masks, T, Hq, Hkv, dh, scale, softcap,
+                                         Opart, LSE, 0, &n, ST(stream));
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    return rc;
 }
 int vidi_xattn_merge(const float* Opart, const float* LSE, int P, int splits_per_rank, int64_t rank_stride_o,
                      int64_t rank_stride_l, int rows, int dh, float gate, int accumulate, float* out, void* stream) {

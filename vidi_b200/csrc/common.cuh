@@ -2,6 +2,7 @@
 // bf16 packing and math.  Hand-written inline PTX (no CUTLASS).  Descriptor bit layouts follow the
 // PTX ISA "tcgen05 matrix/instruction descriptor" tables.
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -21,6 +22,20 @@ void set_error(const char* fmt, ...);
             return (int)_e;                                                                  \
         }                                                                                    \
     } while (0)
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: set it once per (kernel, device), thread-safely
+// (a process may drive several GPUs, e.g. the facade's device="cuda:1"; a racing double set is harmless).
+#define VB_SET_SMEM_ONCE(bytes, ...)                                                                                  \
+    do {                                                                                                              \
+        static std::atomic<unsigned long long> done_{0};                                                              \
+        int dev_ = 0;                                                                                                 \
+        cudaGetDevice(&dev_);                                                                                         \
+        const unsigned long long bit_ = 1ull << (dev_ & 63);                                                          \
+        if (!(done_.load(std::memory_order_acquire) & bit_)) {                                                        \
+            VB_CUDA_CHECK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));     \
+            done_.fetch_or(bit_, std::memory_order_release);                                                          \
+        }                                                                                                             \
+    } while (0)
+
 #define VB_REQUIRE(cond, ...)                                  \
     do {                                                       \
         if (!(cond)) {                                         \

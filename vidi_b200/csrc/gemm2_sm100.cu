@@ -219,11 +219,7 @@ static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const 
     int rc;
     if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
     if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N / 2))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_bf16_kernel<BLOCK_N, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        attr_set = true;
-    }
+    VB_SET_SMEM_ONCE(C::kSmemBytes, gemm2_bf16_kernel<BLOCK_N, LN>);
     const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int max_pairs = num_sms() / 2;

@@ -74,12 +74,14 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 }
 
 int num_sms() {
-    static int n = 0;
+    static std::atomic<int> cache[64];          // per device (a process may drive several GPUs)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }

@@ -13,8 +13,8 @@ int rmsnorm(const void*, int64_t, const void*, void*, int64_t, int, int, float, 
 int residual_norm(void*, int64_t, const void*, int64_t, const void*, const void*, void*, int64_t, int, int, float, int, int,
                   cudaStream_t);
 int embed_gather(const int64_t*, const void*, void*, int, int, int, float, cudaStream_t);
-int xattn_splitkv(const void*, int64_t, const void*, const void*, int64_t, const uint8_t*, int, int, int, int, int, int, float,
-                  float, float*, float*, int, cudaStream_t);
+int xattn_splitkv_seg(const void*, int64_t, const void*, const void*, int64_t, int, int, const int*, const int*, const int*,
+                      const uint8_t* const*, int, int, int, int, float, float, float*, float*, int, int*, cudaStream_t);
 int text_qk_prep(const void*, int64_t, void*, int64_t, void*, int64_t, int, int, int, int, const float*, int, cudaStream_t);
 int xattn_merge2(const float*, const float*, int, int, int64_t, int64_t, float, const float*, const float*, int, int, int64_t, int64_t,
                  float, int, const float*, int, int, void*, const unsigned int*, int, unsigned int, int*, cudaStream_t);
@@ -113,19 +113,26 @@ int text_pass(const VidiTextPass* dp, int64_t* launches, cudaStream_t st) {
         TP(text_qk_prep(s.qkv, qd + 2 * kd, s.qrope, qd, tkv + (int64_t)d.pos0 * tld, tld, T, Hq, Hkv, dh, d.inv_freq, d.pos0, st)); ++n;
         const int window = gm ? ((l % 2 == 0) ? d.sliding_window : 0) : d.sliding_window;
         TP(attn_text(s.qrope, qd, tkv, tkv + kd, tld, T, d.pos0 + T, d.pos0, Hq, Hkv, dh, d.scale, d.attn_softcap, window, s.att, st)); ++n;
-        // cross attention partials of this rank: image, then audio
+        // cross attention partials of this rank: image rows, then audio rows
         const __nv_bfloat16* kvl = reinterpret_cast<const __nv_bfloat16*>(d.stream_kv) + (int64_t)l * d.stream_layer_stride;
+        // both segments in one call (one launch on the tcgen05 path): flat = O [P0+P1][rows][dh] | LSE [P0+P1][rows]
         const float *O[2] = {nullptr, nullptr}, *L[2] = {nullptr, nullptr};
-        float* f = s.flat;
-        for (int i = 0; i < d.nseg; ++i) {
-            const VidiTextSeg& g = d.seg[i];
-            float* op = f;
-            float* ls = f + (int64_t)g.splits * rows * dh;
-            const __nv_bfloat16* kk = kvl + g.row0 * d.stream_ld;
-            TP(xattn_splitkv(s.qkv, qd + 2 * kd, kk, kk + kd, d.stream_ld, g.kmask, T, g.rows, Hq, Hkv, dh, g.splits, d.scale, d.attn_softcap,
-                             op, ls, 0, st)); ++n;
-            O[i] = op; L[i] = ls;
-            f += (int64_t)g.splits * rows * (dh + 1);
+        if (d.nseg > 0) {
+            int row0[2] = {0, 0}, nrows[2] = {0, 0}, sp[2] = {1, 1};
+            const uint8_t* masks[2] = {nullptr, nullptr};
+            int ptot = 0;
+            for (int i = 0; i < d.nseg; ++i) {
+                row0[i] = (int)d.seg[i].row0; nrows[i] = d.seg[i].rows; sp[i] = d.seg[i].splits; masks[i] = d.seg[i].kmask;
+                ptot += sp[i];
+            }
+            float* Oall = s.flat;
+            float* Lall = s.flat + (int64_t)ptot * rows * dh;
+            int nl = 1;
+            TP(xattn_splitkv_seg(s.qkv, qd + 2 * kd, kvl, kvl + kd, d.stream_ld, d.stream_rows, d.nseg, row0, nrows, sp, masks, T, Hq, Hkv, dh,
+                                 d.scale, d.attn_softcap, Oall, Lall, 0, &nl, st));
+            n += nl;
+            O[0] = Oall; L[0] = Lall;
+            if (d.nseg > 1) { O[1] = Oall + (int64_t)sp[0] * rows * dh; L[1] = Lall + (int64_t)sp[0] * rows; }
         }
         // a = bf16(att_text + sum_s gate_s * merge_s): one launch; multi-rank: pre-merge + push to the peers, then flag-wait merge
         const float g0 = d.nseg > 0 ? d.seg[0].gate : 0.f, g1 = d.nseg > 1 ? d.seg[1].gate : 0.f;

@@ -331,6 +331,12 @@ class Vidi15Engine:
             run.layer(l)
         return run.finish()
 
+    def split_plan(self, seg) -> list:
+        """key splits per stream segment: together they fill the SMs once (one launch covers both segments), shared in proportion to
+        the segments' key counts; sized from the per-rank share of the GLOBAL counts so every rank uses the same plan"""
+        c = self.cfg.llm
+        return [max(1, s + self.split_bias) for s in ops.xattn_split_plan([-(-g[4] // self.world) for g in seg], c.kv_heads, self.n_sms)]
+
     def _layer_table(self):
         """HOST array of per-layer weight pointers for vidi_text_pass (built once)"""
         if getattr(self, "_ltab", None) is None:
@@ -373,11 +379,10 @@ class Vidi15Engine:
             d.text_kv, d.text_kv_layer_stride, d.text_kv_ld = tkv.data_ptr(), tkv.stride(0), tkv.stride(1)
         d.stream_kv = kv.data_ptr() if kv.numel() else None
         d.stream_layer_stride, d.stream_ld = (kv.stride(0), kv.stride(1)) if kv.numel() else (0, 2 * c.kv_dim)
-        d.nseg = len(seg)
-        for i, (r0, nr, kmask, gate, n_total) in enumerate(seg):
+        d.nseg, d.stream_rows = len(seg), kv.shape[1]
+        for i, ((r0, nr, kmask, gate, n_total), sp) in enumerate(zip(seg, self.split_plan(seg))):
             sg = d.seg[i]
-            sg.row0, sg.rows, sg.gate = r0, nr, gate
-            sg.splits = max(1, ops.xattn_splits(-(-n_total // self.world), c.kv_heads, self.n_sms) + self.split_bias)
+            sg.row0, sg.rows, sg.gate, sg.splits = r0, nr, gate, sp
             sg.kmask = kmask.data_ptr() if (kmask is not None and kmask.numel()) else None
         d.world, d.rank = self.world, self.rank
         x = self.xchg
@@ -490,9 +495,12 @@ class _TextRun:
         self.rows = self.Tq * c.heads
         dh = c.head_dim
         # one flat fp32 buffer per layer holds every stream's [O | LSE] split partials of this rank
-        self.splits = [max(1, ops.xattn_splits(-(-s[4] // eng.world), c.kv_heads, eng.n_sms) + eng.split_bias) for s in seg]
-        self.sizes = [sp * self.rows * (dh + 1) for sp in self.splits]
-        self.flat = torch.empty(max(1, sum(self.sizes)), device=eng.device, dtype=torch.float32)
+        self.splits = eng.split_plan(seg)
+        ptot = sum(self.splits)
+        # flat = O [P0+P1][rows][dh] | LSE [P0+P1][rows]  (segment 1's partials follow segment 0's: ops.xattn_splitkv_seg)
+        self.flat = torch.empty(max(1, ptot * self.rows * (dh + 1)), device=eng.device, dtype=torch.float32)
+        self.O_all = self.flat[:ptot * self.rows * dh]
+        self.L_all = self.flat[ptot * self.rows * dh:]
         # multi-rank: each rank first reduces its own splits to ONE (O, LSE) partial per stream (xchg.cu), and only those cross ranks:
         #   "p2p"  -- stored straight into every peer's arena over NVLink, merge kernel waits on flags (no NCCL, no host sync)
         #   "nccl" -- one all_gather_into_tensor of the reduced block per layer (used when the arenas cannot be mapped)
@@ -534,16 +542,16 @@ class _TextRun:
             kview, vview = self.krope[:, :kd], self.krope[:, kd:]
         window = (c.sliding_window if l % 2 == 0 else 0) if gm else (getattr(c, "sliding_window", 0) or 0)
         ops.attn_text(self.qrope, kview, vview, pos0, c.heads, c.kv_heads, dh, self.scale, self.cap, window, out=self.att)
-        off = 0
         kvl = self.kv[l]
         srcs = []
-        for (r0, nr, kmask, gate, _), sp, sz in zip(self.seg, self.splits, self.sizes):
-            op = self.flat[off:off + sp * rows * dh]
-            ls = self.flat[off + sp * rows * dh:off + sz]
-            ops.xattn_splitkv(qkv[:, :qd], kvl[r0:r0 + nr, :kd], kvl[r0:r0 + nr, kd:], kmask, c.heads, c.kv_heads, dh,
-                              self.scale, self.cap, sp, opart=op, lse=ls)
-            srcs.append((op, ls, sp))
-            off += sz
+        if self.seg:
+            ops.xattn_splitkv_seg(qkv[:, :qd], kvl[:, :kd], kvl[:, kd:], [(s[0], s[1], s[2]) for s in self.seg], self.splits, c.heads,
+                                  c.kv_heads, dh, self.scale, self.cap, self.O_all, self.L_all)
+            p0 = 0
+            for sp in self.splits:
+                srcs.append((self.O_all[p0 * rows * dh:], self.L_all[p0 * rows:], sp))
+                p0 += sp
+        self.srcs = srcs
         if self.mode == "p2p":
             ops.xchg_push(e.xchg, srcs, rows, dh)
         elif self.mode == "nccl":
@@ -568,10 +576,7 @@ class _TextRun:
                 srcs.append((o, o[rows * dh:], e.world, 1, self.block, self.block, gate))
             a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
         else:
-            srcs, off = [], 0
-            for gate, sp, sz in zip(gates, self.splits, self.sizes):
-                srcs.append((self.flat[off:], self.flat[off + sp * rows * dh:], sp, sp, 0, 0, gate))
-                off += sz
+            srcs = [(o, l_, sp, sp, 0, 0, gate) for (o, l_, sp), gate in zip(self.srcs, gates)]
             a = ops.xattn_merge2(srcs, self.att, self.a, rows, dh)
         ops.gemm(a, L.wo, out=self.y, tag="text")
         w_next = Ls[l + 1].n_in if l + 1 < len(Ls) else e.W.final_norm

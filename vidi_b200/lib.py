@@ -47,6 +47,8 @@ SIGNATURES = {
     "vidi_attn_dense_poly": [_p, _l, _p, _l, _i, _i, _i, _i, _f, _i, _p],
     "vidi_attn_dense_mma": [_p, _l, _i, _i, _i, _p, _l, _i, _i, _i, _i, _f, _p],
     "vidi_xattn_splitkv": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
+    "vidi_xattn_splitkv_seg": [_p, _l, _p, _p, _l, _i, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(_p),
+                               _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_splitkv_mma": [_p, _l, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p],
     "vidi_xattn_merge": [_p, _p, _i, _i, _l, _l, _i, _i, _f, _i, _p, _p],
     "vidi_text_qk_prep": [_p, _l, _p, _l, _p, _l, _i, _i, _i, _i, _p, _i, _p],
@@ -78,7 +80,8 @@ class VidiTextPass(C.Structure):
                 + [("layer_w", C.POINTER(VidiTextLayerW)), ("embed", _p), ("final_norm", _p), ("lm_head", _p), ("inv_freq", _p), ("ids", _p),
                    ("text_kv", _p), ("text_kv_layer_stride", _l), ("text_kv_ld", _l),
                    ("stream_kv", _p), ("stream_layer_stride", _l), ("stream_ld", _l),
-                   ("nseg", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("seq0", C.c_uint32),
+                   ("nseg", C.c_int32), ("stream_rows", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("seq0", C.c_uint32),
+                   ("reserved0", C.c_int32),
                    ("seg", VidiTextSeg * 2), ("peer_data", _p * 16), ("peer_flags", _p * 16), ("cap", _l),
                    ("counter", _p), ("err", _p), ("workspace", _p), ("workspace_bytes", _l), ("logits", _p)])
 

@@ -205,6 +205,22 @@ class DattnGemma2ForCausalLM:
                                  return_state=True)
         return logits, _PrefillState(st["kv"], st["seg"], tc)
 
+    @torch.no_grad()
+    def encode_media(self, images: Optional[torch.Tensor], audios: Optional[torch.Tensor], audio_size: int = 0):
+        """Towers + projectors + the whole image/audio stream pass of ONE video, without any text: returns the state that
+        ``generate(..., media=state)`` runs queries against.  Not in the reference (its streams are recomputed for every ask()); the
+        decomposed attention makes them query-independent (gemma.py:183-202), which the batched VUE runner exploits."""
+        eng = self.engine
+        F = images.shape[0] if images is not None else 0
+        Cn = audios.shape[0] if audios is not None else 0
+        plan = make_plan(self.cfg, F, Cn, audio_size or 0, eng.rank, eng.world)
+        img = self._dev(images[plan.f0:plan.f1]) if images is not None else None
+        aud = self._dev(audios[plan.c0:plan.c1]) if audios is not None else None
+        iv = self._any_nonzero(img) if img is not None else True
+        av = self._any_nonzero(aud) if aud is not None else True
+        S, seg = eng.encode_streams(img, aud, plan, iv, av)
+        return _PrefillState(eng.stream_pass(S), seg, None)
+
     # --- forward -----------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
@@ -266,7 +282,7 @@ class DattnGemma2ForCausalLM:
     # --- generate ----------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, inputs: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None, image_sizes=None,
-                 audios: Optional[torch.Tensor] = None, audio_sizes: Optional[List[int]] = None, **kwargs) -> torch.LongTensor:
+                 audios: Optional[torch.Tensor] = None, audio_sizes: Optional[List[int]] = None, media=None, **kwargs) -> torch.LongTensor:
         """Greedy decoding (the only mode the reference's callers use: do_sample=False, inference.py:40-50).
         Returns only the new token ids, as HF does when generation starts from embeddings (gemma.py:646-655)."""
         if "inputs_embeds" in kwargs:
@@ -288,7 +304,14 @@ class DattnGemma2ForCausalLM:
             img = images[b] if images is not None else None
             aud = audios[b] if audios is not None else None
             asz = int(audio_sizes[b]) if audio_sizes is not None else (aud.shape[0] * self.cfg.aud.nb_max_frames if aud is not None else 0)
-            logits, st = self._prefill_one(ids, img, aud, asz, ids.numel() + max_new, logits_to_keep=1)
+            if media is not None:            # streams of this video already encoded (encode_media): only the text pass runs
+                assert B == 1 and images is None and audios is None, "media= carries one video's streams; pass no images / audios"
+                tc = self.engine.new_text_cache(ids.numel() + max_new)
+                logits = self.engine.text_pass(ids.to(self.device, dtype=torch.int64).contiguous(), media.kv, media.seg, text_cache=tc,
+                                               logits_to_keep=1)
+                st = _PrefillState(media.kv, media.seg, tc)
+            else:
+                logits, st = self._prefill_one(ids, img, aud, asz, ids.numel() + max_new, logits_to_keep=1)
             new = []
             for _ in range(max_new):
                 nxt = int(torch.argmax(logits[-1]))

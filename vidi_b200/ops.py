@@ -329,6 +329,37 @@ def xattn_splits(n_keys: int, hkv: int, n_sms: int = 148) -> int:
     return max(1, min(want, (n_keys + 511) // 512))
 
 
+def xattn_split_plan(n_keys: Sequence[int], hkv: int, n_sms: int = 148) -> list:
+    """key splits for the segments of ONE launch: the total fills the SMs once (n_sms // hkv CTAs per KV head), shared between the
+    segments in proportion to their key counts, at least 1 each and at most one split per 512 keys."""
+    want = max(1, n_sms // max(hkv, 1))
+    caps = [max(1, (max(n, 0) + 511) // 512) for n in n_keys]
+    tot = sum(max(n, 0) for n in n_keys)
+    if len(n_keys) == 1 or tot == 0:
+        return [min(want, c) for c in caps]
+    out = [max(1, min(c, int(round(want * max(n, 0) / tot)))) for n, c in zip(n_keys, caps)]
+    while sum(out) > want and max(out) > 1:
+        i = max(range(len(out)), key=lambda j: out[j])
+        out[i] -= 1
+    return out
+
+
+def xattn_splitkv_seg(q, k, v, segs, splits, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, opart, lse):
+    """Both key segments of a layer in one call (one launch on the tcgen05 path).  k, v: [N, *] views of the layer's K||V cache from
+    row 0; segs: [(row0, rows, kmask or None)]; opart fp32 flat [sum(splits) * T * Hq * dh], lse fp32 flat [sum(splits) * T * Hq]."""
+    L = _lib.load()
+    T, N = q.shape[0], k.shape[0]
+    n = len(segs)
+    assert 1 <= n <= 2 and len(splits) == n and q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16
+    assert opart.dtype == torch.float32 and opart.numel() >= sum(splits) * T * Hq * dh and lse.numel() >= sum(splits) * T * Hq
+    ia = lambda vals: (C.c_int32 * 2)(*(list(vals) + [0] * (2 - n)))
+    masks = (C.c_void_p * 2)(*([(_ptr(m) if (m is not None and m.numel()) else None) for _, _, m in segs] + [None] * (2 - n)))
+    _lib.check(L.vidi_xattn_splitkv_seg(_ptr(q), _rowmajor(q), _ptr(k) if N else None, _ptr(v) if N else None, k.stride(0) if N else 8, N, n,
+                                        ia([s[0] for s in segs]), ia([s[1] for s in segs]), ia(splits), masks, T, Hq, Hkv, dh, scale,
+                                        softcap, _ptr(opart), _ptr(lse), _stream()), "xattn_splitkv_seg")
+    return opart, lse
+
+
 def xattn_splitkv(q, k, v, kmask, Hq: int, Hkv: int, dh: int, scale: float, softcap: float, splits: int,
                   opart=None, lse=None, impl: str = "auto"):
     """q [T, Hq*dh]; k,v [N, *] views with row stride ld -> (opart [splits,T,Hq,dh] f32, lse [splits,T,Hq] f32)."""
@@ -464,7 +495,7 @@ def _instrument(fn):
 for _name in ("rmsnorm", "residual_norm", "layernorm", "mm_finish", "rmsnorm_f32", "patch_im2col", "whisper_im2col1",
               "whisper_im2col2", "pool_s2d", "conv_window_gather", "bilinear_ac", "embed_gather", "sinusoid_split", "split3",
               "cast_bf16", "attn_dense", "xattn_splitkv", "xattn_merge", "rope_inplace", "attn_text", "text_qk_prep", "xattn_merge2",
-              "xattn_premerge", "xchg_push", "xchg_merge"):
+              "xattn_premerge", "xchg_push", "xchg_merge", "xattn_splitkv_seg"):
     globals()[_name] = _instrument(globals()[_name])
 
 
