@@ -43,9 +43,12 @@ def test_gemm_plain(M, N, K, bn):
 
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 256), (256, 128, 128, 128), (300, 520, 288, 256), (1000, 1152, 640, 128),
                                       (4096, 4096, 3584, 256), (5000, 4304, 1152, 256), (129, 72, 64, 128), (46656, 1152, 1152, 128), (3000, 1152, 4304, 192),
-                                      (700, 3456, 1152, 192)])
+                                      (700, 3456, 1152, 192), (3000, 1152, 4304, 256), (700, 3456, 1152, 256), (1030, 1296, 320, 256),
+                                      (513, 264, 128, 256)])
 def test_gemm_2cta(M, N, K, bn):
-    """CTA-pair (cta_group::2) kernel: same contract as the 1-CTA kernel."""
+    """CTA-pair (cta_group::2) kernel: same contract as the 1-CTA kernel.  N not a multiple of block_n exercises the ragged last
+    column tile, which runs a narrower MMA (n_eff = roundup(N - n0, 16): 128 for N = 1152 / 3456, 208 for 4304, 16 for 1296, 8 -> 16 for
+    264) with each CTA of the pair supplying n_eff / 2 rows of W."""
     from vidi_b200 import ops
     a = rnd(M, K, seed=51).to(BF); w = rnd(N, K, scale=0.05, seed=52).to(BF)
     bias = rnd(N, seed=53).float(); res = rnd(M, N, seed=54).to(BF)
@@ -585,3 +588,33 @@ def test_xattn_uncapped_dh128_tcgen05_reference_window(case):
     assert torch.isfinite(out["auto"]).all()
     assert rel_err(out["auto"], ref) < 1e-2, rel_err(out["auto"], ref)
     assert rel_err(out["mma"], ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,glu,act", [
+    (1, 8192, 3584, 0, 0), (32, 8192, 3584, 0, 0), (32, 3584, 4096, 0, 0), (7, 3584, 14336, 0, 0), (24, 28672, 3584, 1, 0),
+    (1, 28672, 3584, 1, 0), (40, 1024, 512, 0, 0), (64, 2048, 512, 2, 0), (5, 25600, 3584, 0, 3), (33, 520, 288, 0, 0), (16, 4096, 1032, 0, 0)])
+def test_gemm_skinny_text_shapes(M, N, K, glu, act):
+    """Weight-streaming GEMM of the text stream (gemm_skinny_sm100.cu: swapped operands, split-K with fixed-order reduction): against
+    fp32 torch and against the general kernel (block_n < 0 forces it); two launches must be bit-identical (deterministic reduction)."""
+    from vidi_b200 import ops
+    from vidi_b200.weights import pack_glu
+    a = rnd(M, K, seed=71).to(BF)
+    if glu:
+        wg = rnd(N // 2, K, scale=0.03, seed=72).to(BF); wu = rnd(N // 2, K, scale=0.03, seed=73).to(BF)
+        w = pack_glu(wg, wu, 256)
+        g = a.float() @ wg.float().t()
+        ref = (F.gelu(g, approximate="tanh") if glu == 1 else F.silu(g)) * (a.float() @ wu.float().t())
+    else:
+        w = rnd(N, K, scale=0.03, seed=72).to(BF)
+        ref = a.float() @ w.float().t()
+        if act == 3:
+            ref = 30.0 * torch.tanh(ref / 30.0)
+    kw = dict(glu=glu, act=act, act_param=30.0, out_fp32=(act == 3))
+    out = ops.gemm(a, w, **kw)
+    out2 = ops.gemm(a, w, **kw)
+    gen = ops.gemm(a, w, block_n=-(256 if glu else 64), **kw)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and torch.equal(out, out2)
+    assert rel_err(out, ref) < 6e-3, rel_err(out, ref)
+    assert rel_err(out, gen) < 6e-3, rel_err(out, gen)
+    assert float((out.float() - ref).abs().max()) < 0.05 * float(ref.abs().max()) + 1e-2

@@ -69,7 +69,7 @@ def dense_case(B, S, H, dh):
     t_2 = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl="v2"))
     rec = dict(kernel="attn_dense", B=B, S=S, H=H, dh=dh, ms=round(t, 4), tflops=round(fl / t / 1e9, 1), v1_tflops=round(fl / t_1 / 1e9, 1), v2_tflops=round(fl / t_2 / 1e9, 1), mma_ms=round(t_m, 4),
                mma_tflops=round(fl / t_m / 1e9, 1))
-    if os.environ.get("VIDI_RUN_UNVALIDATED") == "1":          # parked A/B variants: FMA-pipe exp2 on every N-th score pair
+    if True:                                                    # A/B variants: FMA-pipe exp2 on every N-th score pair
         for n in (2, 3, 4):
             t_p = timeit(lambda: ops.attn_dense(qkv, B, S, H, dh, dh ** -0.5, out=out, impl=f"poly{n}"))
             rec[f"poly{n}_tflops"] = round(fl / t_p / 1e9, 1)
@@ -110,6 +110,17 @@ if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[1] == "one"):
         gemm_case("text_gateup", 32, 28672, 3584, glu=1)
         gemm_case("text_down", 32, 3584, 14336)
         gemm_case("text_down_bn64", 32, 3584, 14336, bn=64)
+    if which in ("all", "text"):
+        # text-stream GEMMs: weight-streaming (swap-AB) kernel vs the general kernel (block_n < 0 forces it), GB/s of W read
+        for name, M, N, K, glu in (("qkv", 32, 8192, 3584, 0), ("o", 32, 3584, 4096, 0), ("gate_up", 32, 28672, 3584, 1), ("down", 32, 3584, 14336, 0),
+                                   ("lm_head", 32, 256000, 3584, 0), ("qkv_dec", 1, 8192, 3584, 0), ("gate_up_dec", 1, 28672, 3584, 1),
+                                   ("down_dec", 1, 3584, 14336, 0), ("lm_head_dec", 1, 256000, 3584, 0)):
+            a = torch.randn(M, K, device="cuda").to(BF); w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
+            out = torch.empty(M, N // 2 if glu else N, device="cuda", dtype=BF)
+            t_s = timeit(lambda: ops.gemm(a, w, out=out, glu=glu, cta2=False))
+            t_g = timeit(lambda: ops.gemm(a, w, out=out, glu=glu, cta2=False, block_n=-(256 if glu else 64)))
+            print(json.dumps(dict(kernel="gemm_text", name=name, M=M, N=N, K=K, skinny_us=round(t_s * 1e3, 1), skinny_gbs=round(N * K * 2 / t_s / 1e6, 1),
+                                  general_us=round(t_g * 1e3, 1), general_gbs=round(N * K * 2 / t_g / 1e6, 1))), flush=True)
     if which in ("all", "attn"):
         for sp in (18, 37, 55, 74):
             xattn_case(32, 126000, sp)

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_generate_gpu.py -m gpu -q --timeout 300 -x -k "xattn or native or vidi7b or multirank or prefill_mini or facade or generate" > gpurun_out/r02_c6_tests.log 2>&1; tail -15 gpurun_out/r02_c6_tests.log
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_generate_gpu.py -m gpu -q --timeout 300 -x -k "xattn or native or vidi7b or multirank or prefill_mini or facade or generate or vue or merge or premerge or peer" > gpurun_out/r02_c6_tests.log 2>&1; tail -15 gpurun_out/r02_c6_tests.log
 L=gpurun_out/r02_c6_bench_ab.log; : > $L
 for v in "--llm-cta2 1" "--llm-cta2 0"; do
   echo "== bench --quick --steps 3 $v" >> $L

@@ -145,7 +145,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 int m_blk, n_blk;
                 tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
                 const int row_a = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M;
-                const int row_b = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                // ragged last column tile: the MMA is issued only n_eff = roundup(N - n0, 16) wide, each CTA supplies n_eff / 2 rows of W
+                const int n_eff = p.ragged_tail ? min(BLOCK_N, ((p.N - n_blk * BLOCK_N + 15) >> 4) << 4) : BLOCK_N;
+                const int row_b = n_blk * BLOCK_N + (int)rank * (n_eff / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
@@ -158,12 +160,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                int m_blk_, n_blk_;
+                tile_coords(tile, num_m, num_n, p.group_m, m_blk_, n_blk_);
+                // N = 1152 / 3456 / 4304 are not multiples of 256: the last column tile runs a narrower MMA instead of multiplying zeros
+                const int n_eff = p.ragged_tail ? min(BLOCK_N, ((p.N - n_blk_ * BLOCK_N + 15) >> 4) << 4) : BLOCK_N;
+                const uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, (uint32_t)n_eff);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -247,6 +253,8 @@ int gemm2_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
     // default: relaxed hand-back (+4.7 % on the tower block, profiles/r02_tower_ab.txt); VIDI_GEMM2_RELAXED=0 restores the release for A/B
     static const int relaxed = getenv("VIDI_GEMM2_RELAXED") ? atoi(getenv("VIDI_GEMM2_RELAXED")) : 1;
     p.relaxed_arrive = relaxed;
+    static const int ragged = getenv("VIDI_GEMM2_RAGGED") ? atoi(getenv("VIDI_GEMM2_RAGGED")) : 1;
+    p.ragged_tail = ragged;
     if (ln_stats || stats_out) VB_REQUIRE(!glu && !out_fp32, "gemm2_bf16_ln: LayerNorm fold / row statistics need a plain bf16 output");
     if (ln_stats) {
         VB_REQUIRE(ln_parts > 0 && ln_colsum != nullptr, "gemm2_bf16_ln: ln_stats needs ln_parts > 0 and ln_colsum");

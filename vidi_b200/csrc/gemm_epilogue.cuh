@@ -33,6 +33,7 @@ struct GemmParams {
     float2* stats_out = nullptr;
     int stats_parts = 0;
     int relaxed_arrive = 0;              // A/B: release the accumulator with a relaxed (not release.cluster) arrive
+    int ragged_tail = 1;                 // A/B: narrow MMA on the ragged last column tile (0: full-width MMA over zero-filled W rows)
 };
 
 // taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;
@@ -100,7 +101,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         const __nv_bfloat16* res_row =
             (p.residual && row_ok) ? p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr : nullptr;
         uint4 rq_next[4];
-        const int c_begin = wg * (BLOCK_N / 2), c_end = (wg + 1) * (BLOCK_N / 2);
+        // columns at and beyond N were never computed when the last tile ran a narrower MMA: stop at the tile's valid width
+        const int c_begin = wg * (BLOCK_N / 2), c_end = min((wg + 1) * (BLOCK_N / 2), p.ragged_tail ? (((p.N - col0 + 31) >> 5) << 5) : BLOCK_N);
         if (res_row && col0 + c_begin + 32 <= p.N) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rq_next[j] = *reinterpret_cast<const uint4*>(res_row + col0 + c_begin + j * 8);

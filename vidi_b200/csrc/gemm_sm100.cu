@@ -12,6 +12,8 @@
 //
 // This one kernel family serves every dense contraction on the Vidi prefill path (SURVEY.md 2.2
 // K1,K2,K5,K8,K9,K12,K13,K14,K17,K18).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb {
@@ -315,10 +317,20 @@ static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, c
     return 0;
 }
 
+bool gemm_skinny_supports(int M, int N, int K, const float* bias, const void* residual, int act, int glu);
+int gemm_skinny(const void*, int64_t, const void*, int64_t, void*, int64_t, int, int, int, int, float, int, int, cudaStream_t);
+
 int gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
               const float* bias, const void* residual, int64_t ldr, int res_mod, int act, float act_param, int out_fp32,
               int glu, int block_n, cudaStream_t st) {
     VB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+    // text-stream shapes (a few rows against a whole weight matrix): weight-streaming kernel with swapped operands
+    // (gemm_skinny_sm100.cu); block_n < 0 forces the general kernel (A/B and tests)
+    static const int skinny = getenv("VIDI_GEMM_SKINNY") ? atoi(getenv("VIDI_GEMM_SKINNY")) : 1;
+    if (skinny && block_n >= 0 && gemm_skinny_supports(M, N, K, bias, residual, act, glu) && ldc % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(C) & 15) == 0)
+        return gemm_skinny(A, lda, W, ldw, C, ldc, M, N, K, act, act_param, out_fp32, glu, st);
+    if (block_n < 0) block_n = -block_n;
     VB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: K/lda/ldw must be multiples of 8 (TMA 16B rows)");
     VB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_bf16: pointers must be 16B aligned");
