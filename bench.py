@@ -403,7 +403,7 @@ def run_ours(args):
                           traffic_src=MEASURED_TRAFFIC_SRC,
                           algorithmic_bytes=int(M_loc * cfg.llm.hidden * 2 + 2 * cfg.llm.inter * cfg.llm.hidden * 2 + M_loc * cfg.llm.inter * 2))
     # replicated text pass alone (the Amdahl term of the multi-GPU run): CUDA events around engine.text_pass on a prebuilt cache
-    text_ms = None
+    text_ms, text_brk = None, None
     if not args.quick:
         _, st_ = eng.prefill(ids_dev, dev_img, dev_mel, asz, n_frames_total=F, n_chunks_total=Cn, return_state=True)
         eng.text_pass(ids_dev, st_["kv"], st_["seg"])
@@ -415,6 +415,15 @@ def run_ours(args):
         b_.record()
         barrier()
         text_ms = round(a_.elapsed_time(b_) / 3, 2)
+        # GPU time by op of one prefill text pass (per-layer Python path with per-op CUDA events; the timed number above is the native path)
+        eng.native_text = False
+        ops.PROFILE, ops.PROFILE_OPS = [], {}
+        eng.text_pass(ids_dev, st_["kv"], st_["seg"])
+        torch.cuda.synchronize()
+        text_brk = {k: round(sum(x.elapsed_time(y) for x, y in v), 3) for k, v in ops.PROFILE_OPS.items()}
+        text_brk["gemm"] = round(sum(e0.elapsed_time(e1) for _, _, e0, e1 in ops.PROFILE), 3)
+        ops.PROFILE, ops.PROFILE_OPS = None, None
+        eng.native_text = True
         del st_
     # decode: q_len = 1 greedy steps on the caches of a prefill, through the same engine.text_pass (native executor);
     # per token the GPU streams the text GEMM weights + lm_head once and this rank's shard of the image/audio K||V cache once
@@ -438,12 +447,33 @@ def run_ours(args):
         b_.record()
         barrier()
         ms_tok = a_.elapsed_time(b_) / n_dec
+        # host cost of one step in isolation (queue drained before each enqueue, so the call never blocks on a full launch queue)
+        t_host = 0.0
+        for _ in range(4):
+            torch.cuda.synchronize()
+            h0 = time.perf_counter()
+            lg = eng.text_pass(nxt, st_["kv"], st_["seg"], text_cache=tc, logits_to_keep=1)
+            t_host += time.perf_counter() - h0
+        torch.cuda.synchronize()
+        t_host *= n_dec / 4
+        # where the GPU time of a text pass goes: one pass through the per-layer Python path with per-op CUDA events
+        eng.native_text = False
+        ops.PROFILE, ops.PROFILE_OPS = [], {}
+        eng.text_pass(nxt, st_["kv"], st_["seg"], text_cache=tc, logits_to_keep=1)
+        torch.cuda.synchronize()
+        brk = {k: round(sum(x.elapsed_time(y) for x, y in v), 3) for k, v in ops.PROFILE_OPS.items()}
+        brk["gemm"] = round(sum(e0.elapsed_time(e1) for _, _, e0, e1 in ops.PROFILE), 3)
+        ops.PROFILE, ops.PROFILE_OPS = None, None
+        eng.native_text = True
         c_ = cfg.llm
         w_bytes = c_.layers * 2 * (c_.hidden * (c_.q_dim + 2 * c_.kv_dim) + c_.q_dim * c_.hidden + 3 * c_.hidden * c_.inter) + 2 * c_.vocab * c_.hidden
         kv_bytes = c_.layers * (plan.n_img + plan.n_aud) * 2 * c_.kv_dim * 2
         decode = dict(tokens_per_s=round(1e3 / ms_tok, 1), ms_per_token=round(ms_tok, 3), host_enqueue_ms_per_token=round(t_host / n_dec * 1e3, 3),
                       steps=n_dec, context_tokens=n_tokens, bytes_per_token=int(w_bytes + kv_bytes), weight_bytes=int(w_bytes), kv_bytes_this_rank=int(kv_bytes),
                       hbm_gbs=round((w_bytes + kv_bytes) / ms_tok / 1e6, 1), hbm_frac=round((w_bytes + kv_bytes) / ms_tok / 1e6 / pk["hbm"], 4),
+                      gpu_ms_by_op_one_step=brk,
+                      xattn_in_step_gbs=round(kv_bytes / brk["xattn_splitkv_seg"] / 1e6, 1) if brk.get("xattn_splitkv_seg") else None,
+                      weight_stream_gbs=round(w_bytes / brk["gemm"] / 1e6, 1) if brk.get("gemm") else None,
                       note="greedy q_len=1 steps against the prefill's caches (text K||V + this rank's image/audio K||V shard); argmax stays on the device")
         del st_, tc
     # end-to-end through the public API with host buffers
@@ -486,7 +516,7 @@ def run_ours(args):
                               "outside this region too); mm_total=(F, C) tells the facade that each rank was handed only its own shard of frames / chunks"),
                 other_ops_ms_per_step={k: v[0] for k, v in sorted(getattr(timed, "by_op", {}).items(), key=lambda kv: -kv[1][0])},
                 gpu_launches=launches, clocks=sampler.result() if sampler else None, load_s=round(t_load, 1),
-                text_pass_ms=text_ms, decode=decode, logits_digest=digest, multi_gpu_parity=parity, exchange=eng.exchange_note,
+                text_pass_ms=text_ms, text_pass_gpu_ms_by_op=text_brk, decode=decode, logits_digest=digest, multi_gpu_parity=parity, exchange=eng.exchange_note,
                 gemm_variant=(("2cta (cta_group::2) on tower/projector" + (" and stream-pass" if eng.llm_cta2 else "") + " sites with M>=1024, 1cta on "
                               + ("" if eng.llm_cta2 else "stream-pass and ") + "text sites") if ops.USE_2CTA else "1cta"))
     print(json.dumps(line), flush=True)
