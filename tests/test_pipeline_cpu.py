@@ -110,3 +110,40 @@ def test_vue_runner_schema_grouping_and_scorer_join(tmp_path):
     assert rows[0]["gt"] == [[405, 990]] and rows[0]["answer"][0] == [400, 1000]
     assert abs(V.temporal_iou(rows[0]["answer"][:1], rows[0]["gt"]) - 585 / 600) < 1e-9
     assert V.temporal_iou(rows[2]["answer"][1:], rows[2]["gt"]) == 1.0
+
+
+def test_media_decoding_follows_load_video_and_load_audio(tmp_path):
+    """media.load_video / load_audio / get_length (vid_utils.py:9-49, inference.py:68-75): a clip written here with OpenCV (10 fps, 37
+    frames, a distinct grey level per frame) is sampled at every round(avg_fps / fps)-th frame from 0; time_range uses linspace over
+    the frame-index range; a 16 kHz 16-bit .wav decodes to float32 / 32768 mono."""
+    import wave
+    import numpy as np
+    cv2 = pytest.importorskip("cv2")
+    from vidi_b200 import media as M
+    path = str(tmp_path / "clip.mp4")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 10.0, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("OpenCV build cannot write mp4v")
+    for i in range(37):
+        wr.write(np.full((48, 64, 3), 5 + 6 * i, np.uint8))
+    wr.release()
+    frames = M.load_video(path, fps=1.0)
+    assert frames.dtype == torch.uint8 and frames.shape == (4, 48, 64, 3)                 # frames 0, 10, 20, 30
+    levels = frames.float().mean((1, 2, 3))
+    assert torch.allclose(levels, torch.tensor([5.0, 65.0, 125.0, 185.0]), atol=4.0)     # lossy codec: right frames, approximate values
+    sub = M.load_video(path, fps=2.0, time_range=(1.0, 3.0))                              # 4 frames over indices 10..30
+    assert sub.shape[0] == 4 and abs(float(sub[0].float().mean()) - 65.0) < 4 and abs(float(sub[-1].float().mean()) - 185.0) < 4
+    assert abs(M.get_length(path) - 3.7) < 0.11
+    wav = str(tmp_path / "a.wav")
+    pcm = (np.sin(np.arange(16000 * 2) * 0.05) * 12000).astype(np.int16)
+    with wave.open(wav, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    audio = M.load_audio(wav, 16000)
+    assert audio.dtype == torch.float32 and audio.shape == (32000,) and torch.allclose(audio, torch.from_numpy(pcm.astype(np.float32) / 32768.0))
+    assert WhisperFeatureExtractorLite(128).audio_size(audio.numel()) == 200
+    # ask_path end to end with a stub model (host pre-processing)
+    tok = FakeTokenizer("gemma2")
+    tok.batch_decode = lambda ids, skip_special_tokens=True: ["0.10-0.50"]
+    out = M.ask_path("a grey ramp.", path, _StubModel([1, 2, 3]), tok, SiglipImageProcessorLite(32), WhisperFeatureExtractorLite(128),
+                     audio_path=wav, device=None)
+    assert out == "00:00:00-00:00:01"

@@ -139,16 +139,19 @@ def one(name):
         "vit_fc2": lambda: gemm_launcher(46656, 1152, 4304, 0),
         "vit_qkv": lambda: gemm_launcher(46656, 3456, 1152, 0),
         "gate_up126k": lambda: gemm_launcher(126000, 28672, 3584, 1, cta2=False),
+        "text_down": lambda: gemm_launcher(32, 3584, 14336, 0, cta2=False),
+        "text_gate_up": lambda: gemm_launcher(32, 28672, 3584, 1, cta2=False),
     }
     if name in cases:
         fn = cases[name]()
     elif name == "attn_vit":
         qkv = torch.randn(64 * 729, 3 * 1152, device="cuda").to(BF); out = torch.empty(64 * 729, 1152, device="cuda", dtype=BF)
         fn = lambda: ops.attn_dense(qkv, 64, 729, 16, 72, 72 ** -0.5, out=out)
-    elif name == "xattn":
+    elif name == "xattn":           # one launch over the image (90 000 keys) and audio (36 000 keys) segments, as the text pass issues it
         q = torch.randn(32, 4096, device="cuda").to(BF); kv = torch.randn(126000, 4096, device="cuda").to(BF)
-        op = torch.empty(37, 32, 16, 256, device="cuda"); ls = torch.empty(37, 32, 16, device="cuda")
-        fn = lambda: ops.xattn_splitkv(q, kv[:, :2048], kv[:, 2048:], None, 16, 8, 256, 1 / 16, 50.0, 37, opart=op, lse=ls)
+        sp = ops.xattn_split_plan([90000, 36000], 8)
+        op = torch.empty(sum(sp) * 32 * 16 * 256, device="cuda"); ls = torch.empty(sum(sp) * 32 * 16, device="cuda")
+        fn = lambda: ops.xattn_splitkv_seg(q, kv[:, :2048], kv[:, 2048:], [(0, 90000, None), (90000, 36000, None)], sp, 16, 8, 256, 1 / 16, 50.0, op, ls)
     elif name == "layernorm":
         x = torch.randn(128 * 729, 1152, device="cuda").to(BF); w = torch.ones(1152, device="cuda"); b = torch.zeros(1152, device="cuda")
         y = torch.empty_like(x)
