@@ -2,7 +2,7 @@
 # Round-2 evidence run (1 GPU, under gpurun): full GPU test suite, smoke, the bench line, the ncu launch list of one C3 step and
 # `ncu --set full` captures of the kernels whose numbers DESIGN.md quotes.  Outputs land in gpurun_out/ and are summarised into profiles/.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 400 > gpurun_out/r02_pytest_gpu_final.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu_final.log
+VIDI_EVIDENCE_DIR=gpurun_out timeout 1500 python -m pytest tests -m gpu -q --timeout 400 --durations=8 > gpurun_out/r02_pytest_gpu_final.log 2>&1; tail -6 gpurun_out/r02_pytest_gpu_final.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_c3_n1_final.json 2> gpurun_out/r02_bench_c3_n1_final.err; tail -c 1500 gpurun_out/r02_bench_c3_n1_final.json
 KRE='regex:^(gemm|attn_|xattn_|layernorm|rmsnorm|residual_norm|mm_finish|pool_s2d|patch_im2col|whisper_im2col|embed_gather|sinusoid|split3|cast_f32|rope|text_qk)'
