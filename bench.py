@@ -115,7 +115,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
-        self.err = None
+        self.err, self.power, self.e0, self.energy_j, self.seconds, self.limit_w = None, [], None, None, None, None
 
     def run(self):
         try:
@@ -130,8 +130,17 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
+            try:
+                self.e0, self.t0 = nv.nvmlDeviceGetTotalEnergyConsumption(h), time.time()      # millijoules since driver load
+                self.limit_w = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+            except Exception:  # noqa: BLE001
+                self.e0 = None
             while not self.stop_flag:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:  # noqa: BLE001
+                    pass
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                     for bit, name in names.items():
@@ -140,13 +149,20 @@ class ClockSampler(threading.Thread):
                 except Exception:  # noqa: BLE001
                     pass
                 time.sleep(0.1)
+            if self.e0 is not None:
+                self.energy_j = (nv.nvmlDeviceGetTotalEnergyConsumption(h) - self.e0) / 1000.0
+                self.seconds = time.time() - self.t0
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
     def result(self):
         s = sorted(self.samples)
+        pw = sorted(self.power)
         return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
-                    samples=len(s), **({"error": self.err} if self.err else {}))
+                    samples=len(s), power_w_median=round(pw[len(pw) // 2], 1) if pw else None, power_limit_w=self.limit_w,
+                    energy_j=round(self.energy_j, 1) if self.energy_j is not None else None,
+                    avg_power_w=round(self.energy_j / self.seconds, 1) if self.energy_j and self.seconds else None,
+                    **({"error": self.err} if self.err else {}))
 
 
 def dist_env():

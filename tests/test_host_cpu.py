@@ -114,13 +114,15 @@ def test_facade_errors_and_sentinel_handling():
 
 def test_postprocess_matches_ask_arithmetic():
     """inference.py:52-66: regex (\\d\\.\\d+)-(\\d\\.\\d+), t = frac * length, HH:MM:SS with int() truncation."""
-    from vidi_b200.postprocess import build_question, format_time_ranges, parse_ranges
+    from vidi_b200.postprocess import format_time_ranges, parse_ranges
+    from vidi_b200.pipeline import DEFAULT_IMAGE_TOKEN, PROMPT_VIDI15
     txt = " 0.10-0.25, 0.5-0.75 and 0.9000-1.0 "
     assert parse_ranges(txt) == [(0.10, 0.25), (0.5, 0.75), (0.9, 1.0)]
     assert format_time_ranges(txt, 3600.0) == "00:06:00-00:15:00, 00:30:00-00:45:00, 00:54:00-01:00:00"
     assert format_time_ranges("0.01-0.02", 25.0) == "00:00:00-00:00:00"
     assert format_time_ranges("no ranges here", 100.0) == ""
-    assert build_question("a dog running.") == "<image>\nDuring which time segments in the video can we see a dog running?"
+    q = "a dog running."
+    assert DEFAULT_IMAGE_TOKEN + "\n" + PROMPT_VIDI15.format(q[:-1]) == "<image>\nDuring which time segments in the video can we see a dog running?"
 
 
 def test_fold_layernorm_algebra():

@@ -6,13 +6,6 @@ import re
 from typing import List, Tuple
 
 _PATTERN = re.compile(r"(\d\.\d+)-(\d\.\d+)")                 # inference.py:55
-PROMPT = "During which time segments in the video can we see {}?"   # inference.py:34
-
-
-def build_question(query: str) -> str:
-    """inference.py:34-35: strip one trailing period, wrap in the fixed prompt, prefix the <image> token."""
-    q = query[:-1] if query.endswith(".") else query
-    return "<image>\n" + PROMPT.format(q)
 
 
 def parse_ranges(text: str) -> List[Tuple[float, float]]:
