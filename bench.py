@@ -399,7 +399,11 @@ def run_ours(args):
     achieved = tot_fl / tot_ms / 1e9 if tot_ms > 0 else 0.0
     roofline = dict(kernel="gemm_bf16_kernel (tcgen05/TMEM/TMA), all stream + tower launches in the timed region",
                     bound="tensor", achieved=round(achieved, 1), peak=pk["tensor"], unit="TFLOP/s",
-                    frac=round(achieved / pk["tensor"], 4), peak_src=f"{pk['src']} bf16_tflops_sustained", traffic=None,
+                    frac=round(achieved / pk["tensor"], 4), peak_src=f"{pk['src']} bf16_tflops_sustained",
+                    # measured dram__bytes (read + write) of ONE launch of the family's largest launch type (gate||up + GeGLU at M = 126 000),
+                    # from the round's committed `ncu --set full` capture; the family total is not a per-launch quantity
+                    traffic=measured_traffic("gate_up126k") if (world == 1 and args.workload == "c3") else None,
+                    traffic_of="gemm_bf16_kernel<256> gate||up launch, M=126000 (algorithmic 4.72 GB)", traffic_src=MEASURED_TRAFFIC_SRC,
                     launches=n_l, share_of_step=round(tot_ms / ms, 4),
                     by_site={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms_per_step=round(v[1] / args.steps, 3), launches=v[2] // args.steps)
                              for k, v in sorted(by_tag.items()) if v[1] > 0})

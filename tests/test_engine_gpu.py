@@ -227,6 +227,37 @@ def test_native_text_pass_equals_per_layer_path(family):
     assert outs[True][0][0].shape == (5, cfg.llm.vocab) and torch.equal(outs[True][3], outs[False][3])
 
 
+def test_prefill_c3_shape_true_dims_depth_cut():
+    """BASELINE config 3's SHAPE features at true 9B hidden dims with the depth cut (SURVEY.md 8c allows layer-subsampled checks): the
+    10 x 10 floor of the resize branch (multimodal.py:175-180, utils.py:152-171) -> 25 tokens per frame, several audio chunks with the
+    last one partial (the floor(size/2) / floor(./5) trimming of multimodal.py:224-236), 32 text tokens; engine vs fp32 oracle."""
+    import dataclasses
+    from vidi_b200.config import vidi15_true_dims
+    cfg = dataclasses.replace(vidi15_true_dims(llm_layers=2, vis_layers=2, aud_layers=1, vocab=4096), max_image_tokens=300)
+    F, Cn = 14, 3
+    assert cfg.image_hw(F) == (10, 10) and cfg.image_tokens(F) == F * 25
+    run_case(cfg, n_frames=F, n_chunks=Cn, n_text=32, audio_size=Cn * 3000 - 1234, check_stages=True)
+
+
+@pytest.mark.parametrize("name,l,N_", [("t", 3600, 10000), ("t", 36000, 10000), ("h", 5, 2)])
+def test_pos_table_at_c3_lengths(name, l, N_):
+    """LearnablePosEmbd at BASELINE config 3's lengths (pos.py:41-58): l = 3600 frames and l = 36 000 audio tokens against
+    mm_time_interval = 10 000; the engine evaluates the fp32 MLP as split-bf16 GEMMs (3 terms) and rms-normalises -- vs the oracle's
+    fp32 evaluation on the rows of a shard in the middle and at both ends."""
+    from oracle import synth, vidi15_ref as R
+    from vidi_b200.config import vidi15_true_dims
+    cfg = vidi15_true_dims(llm_layers=1, vis_layers=2, aud_layers=1, vocab=256)
+    sd, eng = build(cfg)
+    D = cfg.llm.hidden
+    ref = R.xhat(R.pos_embed(sd, f"model.mm_rand_pos_{name}", l, N_, D), cfg.mm_eps)
+    for i0, rows in ((0, min(l, 40)), (l // 2 - 7, min(l, 33)), (max(0, l - 29), min(l, 29))):
+        tab = eng.pos_table(name, rows, i0, l, N_)
+        got, want = tab[:rows].float().cpu(), ref[i0:i0 + rows]
+        # the table is rounded to bf16 after the rms-norm (it is added to bf16 activations): compare at bf16 resolution
+        assert float((got - want).abs().max()) <= 2 ** -7 * float(want.abs().max()) + 1e-3, (name, l, i0, float((got - want).abs().max()))
+        assert rel(got, want) < 4e-3
+
+
 def test_vidi7b_prefill_mini():
     """Vidi-7B (Mistral Dattn): learned-conv pooling, SwiGLU, no post-norms / soft-caps, dh=128."""
     from oracle import synth, vidi7b_ref as R7
