@@ -21,14 +21,16 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TS = false>
 struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
     static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;      // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+    static constexpr int kOutBytes = TS ? 8 * 32 * 128 : 0;          // TMA-store epilogue: one [32 rows x 64 cols] bf16 box per epilogue warp
+    static constexpr int kRing = 200 * 1024 - (TS ? kOutBytes - 8 * 1024 : 0);
+    static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
     static constexpr int kTmemCols = 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -90,15 +92,17 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = r / gm;
 }
 
-template <int BLOCK_N, bool LN>
+template <int BLOCK_N, bool LN, bool TS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-    using C = Cfg<BLOCK_N>;
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+    using C = Cfg<BLOCK_N, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::kStages * C::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint8_t* smem_out = smem + C::kStages * C::kStageBytes;          // TS: 8 x 4 KB staging boxes (1024-aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kOutBytes);
     uint64_t* full_bar = bars;                     // [kStages]  used on the leader only (TMA of both CTAs -> leader MMA)
     uint64_t* empty_bar = bars + C::kStages;       // [kStages]  per CTA (MMA commit multicast -> each producer)
     uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]        per CTA (commit multicast -> each epilogue)
@@ -202,12 +206,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const int row = m_blk * 2 * BLOCK_M + row_in_tile;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
-            epilogue_tile<BLOCK_N, LN>(p, taddr, row, n_blk, wg);
+            epilogue_tile<BLOCK_N, LN, TS>(p, taddr, row, n_blk, wg, &tmap_c, smem_out + (warp - 4) * 4096,
+                                           m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + ew * 32);
             tc_fence_before();
             if (p.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty[acc]);
             else mbar_arrive_leader(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (TS && lane_id() == 0) tma_store_wait_read0();             // the last boxes must have left shared memory before the CTA exits
     }
 
     tc_fence_before();
@@ -218,21 +224,35 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 }
 
-template <int BLOCK_N, bool LN>
-static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N>;
-    CUtensorMap ta, tb;
+template <int BLOCK_N, bool LN, bool TS>
+static int launch_ts(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    using C = Cfg<BLOCK_N, TS>;
+    CUtensorMap ta, tb, tc;
     int rc;
     if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
     if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N / 2))) return rc;
-    VB_SET_SMEM_ONCE(C::kSmemBytes, gemm2_bf16_kernel<BLOCK_N, LN>);
+    tc = ta;
+    if (TS && (rc = make_tmap_2d_bf16(&tc, p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc * 2, 64, 32))) return rc;
+    VB_SET_SMEM_ONCE(C::kSmemBytes, gemm2_bf16_kernel<BLOCK_N, LN, TS>);
     const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int max_pairs = num_sms() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    gemm2_bf16_kernel<BLOCK_N, LN><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, p);
+    gemm2_bf16_kernel<BLOCK_N, LN, TS><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, tc, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// TMA-store epilogue: plain bf16 outputs (no GLU, no fp32) of the 256- and 128-wide tiles (a warp's column half is then a whole number
+// of 64-column boxes), 16-byte aligned rows.  Sustained tower block 1 084 -> 1 224 TF/s, C3 step 4 596 -> 4 365 ms
+// (profiles/r02_ab_tma_store.txt); VIDI_GEMM2_TMASTORE=0 restores the per-thread 16-byte stores for A/B.
+template <int BLOCK_N, bool LN>
+static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    static const int ts = getenv("VIDI_GEMM2_TMASTORE") ? atoi(getenv("VIDI_GEMM2_TMASTORE")) : 1;
+    constexpr bool kCanTS = !LN && (BLOCK_N == 256 || BLOCK_N == 128);
+    if (kCanTS && ts && !p.glu && !p.out_fp32 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 8 == 0)
+        return launch_ts<BLOCK_N, LN, kCanTS>(A, lda, W, ldw, p, st);
+    return launch_ts<BLOCK_N, LN, false>(A, lda, W, ldw, p, st);
 }
 
 }  // namespace g2

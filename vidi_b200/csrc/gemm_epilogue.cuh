@@ -38,8 +38,12 @@ struct GemmParams {
 
 // taddr: TMEM address of this warp's lane quarter at the accumulator's first column; row: global output row of this thread;
 // wg: which half of the tile columns this warp drains; n_blk: tile column index.
-template <int BLOCK_N, bool LN = false>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int n_blk, int wg) {
+// TS: bf16 rows leave through shared memory and TMA tensor stores (UTMASTG): every pair of 32-column chunks is staged as one
+// [32 rows x 64 columns] box in this warp's 4 KB buffer (128-byte swizzle: 16-byte chunk index XOR (row & 7), conflict-free
+// st.shared.v4) and written by ONE cp.async.bulk.tensor store, which also clips rows >= M and columns >= N.
+template <int BLOCK_N, bool LN = false, bool TS = false>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int n_blk, int wg,
+                                              const CUtensorMap* tmap_c = nullptr, uint8_t* stage = nullptr, int row_warp0 = 0) {
     const bool row_ok = row < p.M;
     const int out_cols_total = p.glu ? p.N / 2 : p.N;
     if (p.glu) {
@@ -120,6 +124,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             }
             tmem_ld_wait();
             const int cbase = col0 + c;
+            if (TS && (((c - c_begin) >> 5) & 1) == 0) {          // first chunk of a box: the previous box must have left shared memory
+                if ((threadIdx.x & 31) == 0) tma_store_wait_read0();
+                __syncwarp();
+            }
             if (row_ok && cbase < p.N) {
                 float v[32];
 #pragma unroll
@@ -191,6 +199,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                         #pragma unroll
                         for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = v[j];
                     }
+                } else if (TS) {
+                    // staged: 4 x 16 B of this row into the box of chunk pair (c / 64); statistics as in the direct path
+                    const int half = ((c - c_begin) >> 5) & 1;
+                    uint8_t* srow = stage + (threadIdx.x & 31) * 128;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 q = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                   pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+                        *reinterpret_cast<uint4*>(srow + ((((half << 2) | (j >> 3)) ^ (threadIdx.x & 7)) << 4)) = q;
+                        if (LN && p.stats_out) {
+                            float2 f;
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                f = unpack_bf16(t == 0 ? q.x : t == 1 ? q.y : t == 2 ? q.z : q.w);
+                                if (cbase + j + 2 * t < p.N) { so1 += f.x; so2 = fmaf(f.x, f.x, so2); }
+                                if (cbase + j + 2 * t + 1 < p.N) { so1 += f.y; so2 = fmaf(f.y, f.y, so2); }
+                            }
+                        }
+                    }
                 } else {
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + cbase;
                     if (full) {
@@ -218,6 +245,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                             }
                         }
                     }
+                }
+            }
+            if (TS && ((((c - c_begin) >> 5) & 1) == 1 || c + 32 >= c_end)) {     // box complete (or last, half-filled box of a ragged tile)
+                fence_proxy_async();
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0 && row_warp0 < p.M) {
+                    tma_store_2d(tmap_c, stage, col0 + c_begin + (((c - c_begin) >> 6) << 6), row_warp0);
+                    tma_store_commit();
                 }
             }
         }

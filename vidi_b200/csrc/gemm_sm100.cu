@@ -41,15 +41,16 @@ constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 spare, warps4-11 epilogue (2 column halves x 4 lane quarters)
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TS = false>
 struct GemmCfg {
     static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192) ? 5 : 6;
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kOutBytes = TS ? 8 * 32 * 128 : 0;          // TMA-store epilogue: one [32 rows x 64 cols] bf16 box per epilogue warp
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                      : (2 * BLOCK_N <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int group_m, int& m_blk, int& n_blk) {
@@ -62,16 +63,20 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = r / gm;
 }
 
-template <int BLOCK_N>
+// TS: bf16 outputs (plain and GLU) leave through shared memory and TMA tensor stores.  Each epilogue warp stages a [32 rows x 64 columns]
+// box (128-byte swizzle, conflict-free st.shared.v4) and one lane issues cp.async.bulk.tensor (UTMASTG): full 128-byte lines reach L2
+// instead of 32 half-sector writes per warp instruction, and rows >= M / columns >= N are clipped by the tensor map.
+template <int BLOCK_N, bool TS = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, TS>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* smem_out = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kOutBytes);
     uint64_t* full_bar = bars;                       // [kStages]   TMA -> MMA
     uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]   MMA -> TMA
     uint64_t* tmem_full = bars + 2 * Cfg::kStages;   // [2]         MMA -> epilogue
@@ -161,17 +166,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int acc = 0;
         uint32_t acc_phase = 0;
         const int out_cols_total = p.glu ? p.N / 2 : p.N;
+        uint8_t* stage_box = smem_out + (warp - 4) * 4096;              // TS: this warp's staging box
+        uint8_t* srow = stage_box + lane_id() * 128;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
             mbar_wait_warp(&tmem_full[acc], acc_phase);          // one polling lane per warp (8 pollers instead of 256)
             tc_fence_after();
             const int row = m_blk * BLOCK_M + row_in_tile;
+            const int row_warp0 = m_blk * BLOCK_M + ew * 32;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
             if (p.glu) {
                 constexpr int HALF = BLOCK_N / 2;
                 const int col0 = n_blk * HALF;
+                if (TS) {                                            // previous box of this warp must have left shared memory
+                    if (lane_id() == 0) tma_store_wait_read0();
+                    __syncwarp();
+                }
 #pragma unroll 1
                 for (int c = wg * (HALF / 2); c < (wg + 1) * (HALF / 2); c += 16) {
                     uint32_t g[16], u[16];
@@ -192,7 +204,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             o[j] = pack_bf16(g0 * u0, g1 * u1);
                         }
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0 + c;
-                        if (col0 + c + 16 <= out_cols_total) {
+                        if (TS && HALF / 2 == 64) {                 // this warp's 64 output columns = one box; 16 columns = 2 x 16 B
+                            const int ci = (c - wg * (HALF / 2)) >> 3;
+                            *reinterpret_cast<uint4*>(srow + ((ci ^ (lane_id() & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(srow + (((ci + 1) ^ (lane_id() & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                        } else if (col0 + c + 16 <= out_cols_total) {
                             *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
                             *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
                         } else {
@@ -205,14 +221,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                 }
+                if (TS && HALF / 2 == 64) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane_id() == 0 && row_warp0 < p.M) {
+                        tma_store_2d(&tmap_c, stage_box, col0 + wg * (HALF / 2), row_warp0);
+                        tma_store_commit();
+                    }
+                }
             } else {
                 const int col0 = n_blk * BLOCK_N;
+                const int c_begin = wg * (BLOCK_N / 2);
 #pragma unroll 1
                 for (int c = wg * (BLOCK_N / 2); c < (wg + 1) * (BLOCK_N / 2); c += 32) {
                     uint32_t r[32];
                     tmem_ld_32x32b_x32(taddr + c, r);
                     tmem_ld_wait();
                     const int cbase = col0 + c;
+                    if (TS && (((c - c_begin) >> 5) & 1) == 0) {      // first chunk of a box: the previous box must have left shared memory
+                        if (lane_id() == 0) tma_store_wait_read0();
+                        __syncwarp();
+                    }
                     if (row_ok && cbase < p.N) {
                         float v[32];
 #pragma unroll
@@ -271,6 +300,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 #pragma unroll
                                 for (int j = 0; j < 32; ++j) if (cbase + j < p.N) dst[j] = v[j];
                             }
+                        } else if (TS) {
+                            const int half = ((c - c_begin) >> 5) & 1;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                *reinterpret_cast<uint4*>(srow + ((((half << 2) | (j >> 3)) ^ (lane_id() & 7)) << 4)) =
+                                    make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                               pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
                         } else {
                             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + cbase;
                             if (full) {
@@ -285,12 +321,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                     }
+                    if (TS && !p.out_fp32 && ((((c - c_begin) >> 5) & 1) == 1)) {     // box complete
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane_id() == 0 && row_warp0 < p.M) {
+                            tma_store_2d(&tmap_c, stage_box, col0 + c_begin + (((c - c_begin) >> 6) << 6), row_warp0);
+                            tma_store_commit();
+                        }
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (TS && lane_id() == 0) tma_store_wait_read0();             // the last boxes must have left shared memory before the CTA exits
     }
 
     tc_fence_before();
@@ -301,20 +346,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
-template <int BLOCK_N>
-static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
-    using Cfg = GemmCfg<BLOCK_N>;
-    CUtensorMap ta, tb;
+template <int BLOCK_N, bool TS>
+static int launch_gemm_ts(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BLOCK_N, TS>;
+    CUtensorMap ta, tb, tc;
     int rc;
     if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
     if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N))) return rc;
-    VB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm_bf16_kernel<BLOCK_N>);
+    tc = ta;
+    if (TS && (rc = make_tmap_2d_bf16(&tc, p.C, (uint64_t)(p.glu ? p.N / 2 : p.N), (uint64_t)p.M, (uint64_t)p.ldc * 2, 64, 32))) return rc;
+    VB_SET_SMEM_ONCE(Cfg::kSmemBytes, gemm_bf16_kernel<BLOCK_N, TS>);
     const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M, num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_bf16_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    gemm_bf16_kernel<BLOCK_N, TS><<<grid, kNumThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// TMA-store epilogue for bf16 outputs of the 256- and 128-wide tiles (a warp's column half is then a whole number of 64-column boxes);
+// VIDI_GEMM_TMASTORE=0 restores the per-thread 16-byte stores for A/B.
+template <int BLOCK_N>
+static int launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
+    static const int ts = getenv("VIDI_GEMM_TMASTORE") ? atoi(getenv("VIDI_GEMM_TMASTORE")) : 1;
+    constexpr bool kCanTS = BLOCK_N == 256 || BLOCK_N == 128;
+    if (kCanTS && ts && !p.out_fp32 && (!p.glu || BLOCK_N == 256) && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 8 == 0)
+        return launch_gemm_ts<BLOCK_N, kCanTS>(A, lda, W, ldw, p, st);
+    return launch_gemm_ts<BLOCK_N, false>(A, lda, W, ldw, p, st);
 }
 
 bool gemm_skinny_supports(int M, int N, int K, const float* bias, const void* residual, int act, int glu);

@@ -2,6 +2,9 @@
 // LayerNorm with bias, the fused multimodal "embed finish" pass, and the (O,LSE) partial merge is in xattn.cu.
 // One warp per row, 128-bit loads/stores, fp32 statistics with warp-shuffle reductions; rows are kept packed in
 // registers between the statistic pass and the write pass so every byte crosses HBM exactly once.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb {
