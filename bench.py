@@ -397,13 +397,14 @@ def run_ours(args):
     n_l = sum(v[2] for k, v in by_tag.items() if k != "text")
     pk = peaks()
     achieved = tot_fl / tot_ms / 1e9 if tot_ms > 0 else 0.0
-    roofline = dict(kernel="gemm_bf16_kernel (tcgen05/TMEM/TMA), all stream + tower launches in the timed region",
+    roofline = dict(kernel="gemm2_bf16_kernel / gemm_bf16_kernel (tcgen05 cta_group::2 and ::1, TMEM accumulators, TMA loads + TMA-store epilogue), "
+                           "all stream + tower launches in the timed region",
                     bound="tensor", achieved=round(achieved, 1), peak=pk["tensor"], unit="TFLOP/s",
                     frac=round(achieved / pk["tensor"], 4), peak_src=f"{pk['src']} bf16_tflops_sustained",
                     # measured dram__bytes (read + write) of ONE launch of the family's largest launch type (gate||up + GeGLU at M = 126 000),
                     # from the round's committed `ncu --set full` capture; the family total is not a per-launch quantity
-                    traffic=measured_traffic("gate_up126k") if (world == 1 and args.workload == "c3") else None,
-                    traffic_of="gemm_bf16_kernel<256> gate||up launch, M=126000 (algorithmic 4.72 GB)", traffic_src=MEASURED_TRAFFIC_SRC,
+                    traffic=measured_traffic("gate_up126k_2cta" if eng.llm_cta2 else "gate_up126k") if (world == 1 and args.workload == "c3") else None,
+                    traffic_of="gate||up + GeGLU launch of the stream pass, M=126000 (algorithmic 4.72 GB)", traffic_src=MEASURED_TRAFFIC_SRC,
                     launches=n_l, share_of_step=round(tot_ms / ms, 4),
                     by_site={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms_per_step=round(v[1] / args.steps, 3), launches=v[2] // args.steps)
                              for k, v in sorted(by_tag.items()) if v[1] > 0})
@@ -414,12 +415,14 @@ def run_ours(args):
         M_loc = plan.n_img + plan.n_aud
         fl = 2.0 * M_loc * (2 * cfg.llm.inter) * cfg.llm.hidden
         avg_ms = gu[1] / gu[2]
-        top_launch = dict(kernel="gemm_bf16_kernel<256> GeGLU epilogue", shape=[M_loc, 2 * cfg.llm.inter, cfg.llm.hidden], bound="tensor",
+        tkey = "gate_up126k_2cta" if eng.llm_cta2 else "gate_up126k"
+        top_launch = dict(kernel=("gemm2_bf16_kernel<256> (CTA pair)" if eng.llm_cta2 else "gemm_bf16_kernel<256>") + " GeGLU epilogue, TMA store",
+                          shape=[M_loc, 2 * cfg.llm.inter, cfg.llm.hidden], bound="tensor",
                           achieved=round(fl / avg_ms / 1e9, 1), peak=pk["tensor"], unit="TFLOP/s", frac=round(fl / avg_ms / 1e9 / pk["tensor"], 4),
                           ms_per_launch=round(avg_ms, 3), launches_per_step=gu[2] // args.steps,
                           # dram__bytes of this launch from the round's committed ncu capture (profiles/ncu_traffic.json, written by
                           # tools/ncu_traffic.py from an `ncu --set full` run of tools/bench_kernels.py); never a typed-in constant
-                          traffic=measured_traffic("gate_up126k") if (world == 1 and args.workload == "c3") else None,
+                          traffic=measured_traffic(tkey) if (world == 1 and args.workload == "c3") else None,
                           traffic_src=MEASURED_TRAFFIC_SRC,
                           algorithmic_bytes=int(M_loc * cfg.llm.hidden * 2 + 2 * cfg.llm.inter * cfg.llm.hidden * 2 + M_loc * cfg.llm.inter * 2))
     # replicated text pass alone (the Amdahl term of the multi-GPU run): CUDA events around engine.text_pass on a prebuilt cache

@@ -139,6 +139,8 @@ def one(name):
         "vit_fc2": lambda: gemm_launcher(46656, 1152, 4304, 0),
         "vit_qkv": lambda: gemm_launcher(46656, 3456, 1152, 0),
         "gate_up126k": lambda: gemm_launcher(126000, 28672, 3584, 1, cta2=False),
+        "gate_up126k_2cta": lambda: gemm_launcher(126000, 28672, 3584, 1, cta2=True),
+        "vit_fc2_2cta_res": lambda: gemm_res_launcher(93312, 1152, 4304),
         "text_down": lambda: gemm_launcher(32, 3584, 14336, 0, cta2=False),
         "text_gate_up": lambda: gemm_launcher(32, 28672, 3584, 1, cta2=False),
     }
@@ -165,6 +167,13 @@ def one(name):
     for _ in range(5):
         fn()
     torch.cuda.synchronize()
+
+
+def gemm_res_launcher(M, N, K):
+    """in-place residual GEMM of a tower block (x += a W^T + b): TMA-store epilogue with the residual rows fetched by TMA"""
+    a = torch.randn(M, K, device="cuda").to(BF); w = (torch.randn(N, K, device="cuda") * 0.02).to(BF)
+    x = torch.randn(M, N, device="cuda").to(BF); b = torch.randn(N, device="cuda") * 0.02
+    return lambda: ops.gemm(a, w, bias=b, residual=x, out=x, cta2=True)
 
 
 def gemm_launcher(M, N, K, glu, cta2=None):

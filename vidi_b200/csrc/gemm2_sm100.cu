@@ -21,16 +21,17 @@ constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 384;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
-template <int BLOCK_N, bool TS = false>
+template <int BLOCK_N, bool TS = false, bool RT = false>
 struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;            // 16 KB
     static constexpr int kBBytes = (BLOCK_N / 2) * BLOCK_K * 2;      // this CTA's half of W
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kOutBytes = TS ? 8 * 32 * 128 : 0;          // TMA-store epilogue: one [32 rows x 64 cols] bf16 box per epilogue warp
-    static constexpr int kRing = 200 * 1024 - (TS ? kOutBytes - 8 * 1024 : 0);
+    // TMA-store epilogue: one [32 rows x 64 cols] bf16 box per epilogue warp; RT (residual by TMA): one box per 64 columns of the warp's half
+    static constexpr int kOutBytes = RT ? 8 * (BLOCK_N / 128) * 4096 : TS ? 8 * 4096 : 0;
+    static constexpr int kRing = RT ? (BLOCK_N == 256 ? 160 : 176) * 1024 : TS ? 176 * 1024 : 200 * 1024;
     static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
     static constexpr int kTmemCols = 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 + 512 + (RT ? 128 : 0);
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -92,11 +93,11 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
     n_blk = r / gm;
 }
 
-template <int BLOCK_N, bool LN, bool TS = false>
+template <int BLOCK_N, bool LN, bool TS = false, bool RT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
-    using C = Cfg<BLOCK_N, TS>;
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
+    using C = Cfg<BLOCK_N, TS, RT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -108,6 +109,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * C::kStages;   // [2]        per CTA (commit multicast -> each epilogue)
     uint64_t* tmem_empty = tmem_full + 2;          // [2]        used on the leader only (both epilogues -> MMA)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* res_bar = tmem_empty + 4;            // [8 warps][2 boxes]  RT: residual boxes landed (per CTA)
 
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();
@@ -132,6 +134,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 2 * 256);
         }
+        if (RT)
+            for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2sm<C::kTmemCols>(tmem_ptr);
@@ -198,16 +202,33 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int wg = (warp - 4) >> 2;
         const int row_in_tile = (int)rank * BLOCK_M + ew * 32 + lane_id();
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, rphase = 0;
+        constexpr int NBOX = BLOCK_N / 128;            // 64-column boxes per warp (its column half)
+        uint8_t* my_stage = smem_out + (warp - 4) * (RT ? NBOX * 4096 : 4096);
+        uint64_t* my_rbar = res_bar + (warp - 4) * 2;
         for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             int m_blk, n_blk;
             tile_coords(tile, num_m, num_n, p.group_m, m_blk, n_blk);
+            const int row_warp0 = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + ew * 32;
+            if (RT) {
+                // the residual boxes of this tile do not depend on the accumulator: fetch them while the MMAs still run
+                if (lane_id() == 0) {
+                    tma_store_wait_read0();                       // this warp's earlier stores have left its buffers
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b) {
+                        mbar_expect_tx(&my_rbar[b], 4096);
+                        tma_load_2d(my_stage + b * 4096, &tmap_r, &my_rbar[b], n_blk * BLOCK_N + wg * (BLOCK_N / 2) + b * 64, row_warp0,
+                                    kEvictFirst);
+                    }
+                }
+                __syncwarp();
+            }
             mbar_wait_warp(&tmem_full[acc], acc_phase);          // one polling lane per warp
             tc_fence_after();
             const int row = m_blk * 2 * BLOCK_M + row_in_tile;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(ew * 32) << 16);
-            epilogue_tile<BLOCK_N, LN, TS>(p, taddr, row, n_blk, wg, &tmap_c, smem_out + (warp - 4) * 4096,
-                                           m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + ew * 32);
+            epilogue_tile<BLOCK_N, LN, TS, RT>(p, taddr, row, n_blk, wg, &tmap_c, my_stage, row_warp0, my_rbar, rphase);
+            rphase ^= 1;
             tc_fence_before();
             if (p.relaxed_arrive) mbar_arrive_leader_relaxed(&tmem_empty[acc]);
             else mbar_arrive_leader(&tmem_empty[acc]);
@@ -224,21 +245,23 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
 }
 
-template <int BLOCK_N, bool LN, bool TS>
+template <int BLOCK_N, bool LN, bool TS, bool RT = false>
 static int launch_ts(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
-    using C = Cfg<BLOCK_N, TS>;
-    CUtensorMap ta, tb, tc;
+    using C = Cfg<BLOCK_N, TS, RT>;
+    CUtensorMap ta, tb, tc, tr;
     int rc;
     if ((rc = make_tmap_2d_bf16(&ta, A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, BLOCK_K, BLOCK_M))) return rc;
     if ((rc = make_tmap_2d_bf16(&tb, W, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N / 2))) return rc;
     tc = ta;
-    if (TS && (rc = make_tmap_2d_bf16(&tc, p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc * 2, 64, 32))) return rc;
-    VB_SET_SMEM_ONCE(C::kSmemBytes, gemm2_bf16_kernel<BLOCK_N, LN, TS>);
+    if (TS && (rc = make_tmap_2d_bf16(&tc, p.C, (uint64_t)(p.glu ? p.N / 2 : p.N), (uint64_t)p.M, (uint64_t)p.ldc * 2, 64, 32))) return rc;
+    tr = tc;
+    if (RT && (rc = make_tmap_2d_bf16(&tr, p.residual, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldr * 2, 64, 32))) return rc;
+    VB_SET_SMEM_ONCE(C::kSmemBytes, gemm2_bf16_kernel<BLOCK_N, LN, TS, RT>);
     const int num_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int tiles = num_m * num_n;
     const int max_pairs = num_sms() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    gemm2_bf16_kernel<BLOCK_N, LN, TS><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, tc, p);
+    gemm2_bf16_kernel<BLOCK_N, LN, TS, RT><<<2 * pairs, kNumThreads, C::kSmemBytes, st>>>(ta, tb, tc, tr, p);
     VB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -250,8 +273,13 @@ template <int BLOCK_N, bool LN>
 static int launch(const void* A, int64_t lda, const void* W, int64_t ldw, const GemmParams& p, cudaStream_t st) {
     static const int ts = getenv("VIDI_GEMM2_TMASTORE") ? atoi(getenv("VIDI_GEMM2_TMASTORE")) : 1;
     constexpr bool kCanTS = !LN && (BLOCK_N == 256 || BLOCK_N == 128);
-    if (kCanTS && ts && !p.glu && !p.out_fp32 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 8 == 0)
+    if (kCanTS && ts && (!p.glu || BLOCK_N == 256) && !p.out_fp32 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 8 == 0) {
+        // residual rows by TMA too (row-aligned residual only; the position-embedding add with res_mod keeps the register path)
+        static const int rt = getenv("VIDI_GEMM2_RESTMA") ? atoi(getenv("VIDI_GEMM2_RESTMA")) : 1;
+        if (rt && !p.glu && p.residual && p.res_mod == 0 && p.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)
+            return launch_ts<BLOCK_N, LN, kCanTS, kCanTS>(A, lda, W, ldw, p, st);
         return launch_ts<BLOCK_N, LN, kCanTS>(A, lda, W, ldw, p, st);
+    }
     return launch_ts<BLOCK_N, LN, false>(A, lda, W, ldw, p, st);
 }
 

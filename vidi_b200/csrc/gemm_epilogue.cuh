@@ -41,14 +41,24 @@ struct GemmParams {
 // TS: bf16 rows leave through shared memory and TMA tensor stores (UTMASTG): every pair of 32-column chunks is staged as one
 // [32 rows x 64 columns] box in this warp's 4 KB buffer (128-byte swizzle: 16-byte chunk index XOR (row & 7), conflict-free
 // st.shared.v4) and written by ONE cp.async.bulk.tensor store, which also clips rows >= M and columns >= N.
-template <int BLOCK_N, bool LN = false, bool TS = false>
+// RT (implies TS): the residual rows also travel by TMA.  Before the accumulator is even ready, one lane fetches the residual box(es) of
+// this warp's column half into the staging buffers (one 4 KB buffer per box, mbarrier rbar[b]); each thread then reads ITS 16-byte
+// slots, adds, and writes the result back in place, and the same buffer leaves through the TMA store -- no per-thread row-strided
+// global loads (32 sector requests per warp instruction) are left in the epilogue.
+template <int BLOCK_N, bool LN = false, bool TS = false, bool RT = false>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int row, int n_blk, int wg,
-                                              const CUtensorMap* tmap_c = nullptr, uint8_t* stage = nullptr, int row_warp0 = 0) {
+                                              const CUtensorMap* tmap_c = nullptr, uint8_t* stage = nullptr, int row_warp0 = 0,
+                                              uint64_t* rbar = nullptr, uint32_t rphase = 0) {
     const bool row_ok = row < p.M;
     const int out_cols_total = p.glu ? p.N / 2 : p.N;
     if (p.glu) {
         constexpr int HALF = BLOCK_N / 2;
+        constexpr bool GTS = TS && !RT && HALF / 2 == 64;       // this warp's 64 output columns = one TMA-store box (256-wide tiles)
         const int col0 = n_blk * HALF;
+        if (GTS) {                                              // previous box of this warp must have left shared memory
+            if ((threadIdx.x & 31) == 0) tma_store_wait_read0();
+            __syncwarp();
+        }
 #pragma unroll 1
         for (int c = wg * (HALF / 2); c < (wg + 1) * (HALF / 2); c += 16) {
             uint32_t g[16], u[16];
@@ -69,7 +79,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                     o[j] = pack_bf16(g0 * u0, g1 * u1);
                 }
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)row * p.ldc + col0 + c;
-                if (col0 + c + 16 <= out_cols_total) {
+                if (GTS) {
+                    uint8_t* srow = stage + (threadIdx.x & 31) * 128;
+                    const int ci = (c - wg * (HALF / 2)) >> 3;
+                    *reinterpret_cast<uint4*>(srow + ((ci ^ (threadIdx.x & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(srow + (((ci + 1) ^ (threadIdx.x & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+                } else if (col0 + c + 16 <= out_cols_total) {
                     *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
                     *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]);
                 } else {
@@ -80,6 +95,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                         if (col0 + c + 2 * j + 1 < out_cols_total) dst[2 * j + 1] = pr.y;
                     }
                 }
+            }
+        }
+        if (GTS) {
+            fence_proxy_async();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0 && row_warp0 < p.M) {
+                tma_store_2d(tmap_c, stage, col0 + wg * (HALF / 2), row_warp0);
+                tma_store_commit();
             }
         }
     } else {
@@ -103,7 +126,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         // The residual row segment of chunk c+1 is requested before chunk c is processed, so its HBM latency overlaps the
         // TMEM load + math + stores of the current chunk instead of serialising four ~1 us round trips per tile.
         const __nv_bfloat16* res_row =
-            (p.residual && row_ok) ? p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr : nullptr;
+            (!RT && p.residual && row_ok) ? p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr : nullptr;
         uint4 rq_next[4];
         // columns at and beyond N were never computed when the last tile ran a narrower MMA: stop at the tile's valid width
         const int c_begin = wg * (BLOCK_N / 2), c_end = min((wg + 1) * (BLOCK_N / 2), p.ragged_tail ? (((p.N - col0 + 31) >> 5) << 5) : BLOCK_N);
@@ -124,10 +147,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             }
             tmem_ld_wait();
             const int cbase = col0 + c;
-            if (TS && (((c - c_begin) >> 5) & 1) == 0) {          // first chunk of a box: the previous box must have left shared memory
+            if (TS && !RT && (((c - c_begin) >> 5) & 1) == 0) {   // first chunk of a box: the previous box must have left shared memory
                 if ((threadIdx.x & 31) == 0) tma_store_wait_read0();
                 __syncwarp();
             }
+            uint8_t* sbox = RT ? stage + ((c - c_begin) >> 6) * 4096 : stage;      // RT: one buffer per box of this column half
+            if (RT && (((c - c_begin) >> 5) & 1) == 0) mbar_wait(&rbar[(c - c_begin) >> 6], rphase);   // residual box has landed
             if (row_ok && cbase < p.N) {
                 float v[32];
 #pragma unroll
@@ -172,7 +197,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
                 }
-                if (p.residual) {
+                if (RT) {
+                    const int half = ((c - c_begin) >> 5) & 1;
+                    const uint8_t* rrow = sbox + (threadIdx.x & 31) * 128;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(rrow + ((((half << 2) | (j >> 3)) ^ (threadIdx.x & 7)) << 4));
+                        float2 f;
+                        f = unpack_bf16(q.x); v[j] += f.x; v[j + 1] += f.y;
+                        f = unpack_bf16(q.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                        f = unpack_bf16(q.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                        f = unpack_bf16(q.w); v[j + 6] += f.x; v[j + 7] += f.y;
+                    }
+                } else if (p.residual) {
                     const __nv_bfloat16* rp = p.residual + (int64_t)(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr + cbase;
                     if (full) {
 #pragma unroll
@@ -202,7 +239,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                 } else if (TS) {
                     // staged: 4 x 16 B of this row into the box of chunk pair (c / 64); statistics as in the direct path
                     const int half = ((c - c_begin) >> 5) & 1;
-                    uint8_t* srow = stage + (threadIdx.x & 31) * 128;
+                    uint8_t* srow = sbox + (threadIdx.x & 31) * 128;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         const uint4 q = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
@@ -251,10 +288,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
                 fence_proxy_async();
                 __syncwarp();
                 if ((threadIdx.x & 31) == 0 && row_warp0 < p.M) {
-                    tma_store_2d(tmap_c, stage, col0 + c_begin + (((c - c_begin) >> 6) << 6), row_warp0);
+                    tma_store_2d(tmap_c, sbox, col0 + c_begin + (((c - c_begin) >> 6) << 6), row_warp0);
                     tma_store_commit();
                 }
             }
+        }
+        if (RT) {                // a box the ragged tile never touched still has a residual load in flight: consume its barrier phase
+            constexpr int NBOX = BLOCK_N / 128;
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b)
+                if (c_begin + b * 64 >= c_end) mbar_wait(&rbar[b], rphase);
         }
         if (LN && p.stats_out && row_ok) p.stats_out[(int64_t)row * p.stats_parts + n_blk * 2 + wg] = make_float2(so1, so2);
     }

@@ -110,9 +110,10 @@ class Vidi15Engine:
         # torch.tensor(hidden**0.5, dtype=act): the normaliser is rounded to the activation dtype (gemma.py:353); Mistral has none
         self.normalizer = float(torch.tensor(cfg.llm.hidden ** 0.5, dtype=BF16).float()) if self.gemma else 1.0
         self.glu = ops.GLU_GELU_TANH if self.gemma else ops.GLU_SILU
-        # GEMM variant per site, from same-box A/B runs of the full step (profiles/): the CTA-pair kernel wins on the tower /
-        # projector shapes (K=1152..5120), the 1-CTA kernel sustains more on the long stream-pass GEMMs at M ~ 1e5.
-        self.llm_cta2 = False
+        # GEMM variant per site, from same-box A/B runs of the full step (profiles/).  Round 1 and early round 2: the CTA-pair kernel won on
+        # the tower / projector shapes only and lost 1-8 % on the stream-pass GEMMs at M ~ 1e5; with the TMA-store epilogue in both kernels
+        # the pair kernel wins there too (4 159 / 4 176 vs 4 197 ms/step, gate||up 1 274 -> 1 322 TF/s: profiles/r02_ab_llm_cta2_tmastore.txt).
+        self.llm_cta2 = True
         # Optional: text pass on a side stream, one layer behind the stream pass (see prefill).  Measured NEGATIVE on B200
         # (profiles/r01_ab_text_overlap_{1,2}gpu.txt: +0.5 % / +2 % step time): the ~700 small kernels that slip in between the
         # persistent GEMMs delay those kernels' CTAs more than the hidden text latency is worth.  Kept off by default.
