@@ -278,6 +278,10 @@ class Vidi15Engine:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
+    def _llm_cta2(self):
+        """GEMM variant of the stream-pass sites: None = automatic (CTA pair for M >= 1024 and 128..256-wide tiles), False = always 1-CTA"""
+        return None if self.llm_cta2 else False
+
     def stream_pass(self, S: torch.Tensor, kv: Optional[torch.Tensor] = None, on_kv=None) -> torch.Tensor:
         """S [n, D] (modified in place) -> K||V cache [L, n, 2*kv_dim] bf16.
         Per layer (gemma.py:183-202 with Q5/Q6 of SURVEY 3.4 dropped): K||V = G(S,w_in) W_kv^T;
@@ -294,18 +298,18 @@ class Vidi15Engine:
         y = torch.empty_like(S)
         g = torch.empty(n, c.inter, device=self.device, dtype=BF16)
         for l, L in enumerate(Ls):
-            ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv", cta2=self.llm_cta2)
+            ops.gemm(h, L.wkv, out=kv[l], tag="llm_kv", cta2=self._llm_cta2())
             if on_kv is not None:
                 on_kv(l)                 # K||V of layer l is enqueued: the text stream may consume it
             if l == len(Ls) - 1:
                 break
-            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo", cta2=self.llm_cta2)
+            ops.gemm(kv[l][:, c.kv_dim:], L.wo_fold, out=y, tag="llm_vo", cta2=self._llm_cta2())
             if gm:      # S += G(y, w_post); h = G(S, w_preff)          (gemma.py:198-202,116-118)
                 ops.residual_norm(S, y, L.n_post, L.n_preff, h, c.rms_eps, 1, True)
             else:       # S += y; h = norm(S, w_post_attention)          (mistral.py:223-225,131-133)
                 ops.residual_norm(S, y, None, L.n_post, h, c.rms_eps, 0, False)
-            ops.gemm(h, L.wgu, glu=self.glu, out=g, tag="llm_gateup", cta2=self.llm_cta2)
-            ops.gemm(g, L.wd, out=y, tag="llm_down", cta2=self.llm_cta2)
+            ops.gemm(h, L.wgu, glu=self.glu, out=g, tag="llm_gateup", cta2=self._llm_cta2())
+            ops.gemm(g, L.wd, out=y, tag="llm_down", cta2=self._llm_cta2())
             if gm:
                 ops.residual_norm(S, y, L.n_postff, Ls[l + 1].n_in, h, c.rms_eps, 1, True)
             else:
