@@ -313,9 +313,14 @@ int gemm2_bf16_ln(const void* A, int64_t lda, const void* W, int64_t ldw, void* 
         p.stats_out = reinterpret_cast<float2*>(stats_out);
         p.stats_parts = 2 * ((N + block_n - 1) / block_n);
     }
-    {   // pair-blocks (256 rows) per L2-resident group, same 48 MB budget as the 1-CTA kernel
+    {   // pair-blocks (256 rows) per L2-resident group.  Measured in-step on C3 (profiles/r02_ab_l2_group.txt): 48 / 32 / 24 / 16 MB of A
+        // rows per group -> 4 112 / 4 056 / 4 070 / 4 100 ms per step; the stream-pass sites (K >= 2048) are best at 32 MB (gate||up
+        // 1 349 -> 1 388 TF/s, DRAM reads of that launch 26.7 -> ~20 GB), the K = 1152 / 1280 tower sites at 16 MB (1 286 -> 1 322 TF/s).
+        // The A panel competes with W tiles, the output stream and -- the L2 being two die-local halves -- a second copy of itself.
         const int64_t per_block = (int64_t)2 * g2::BLOCK_M * K * 2;
-        int64_t gm = (48ll << 20) / per_block;
+        static const int l2_mb_env = getenv("VIDI_GEMM2_L2MB") ? atoi(getenv("VIDI_GEMM2_L2MB")) : 0;
+        const int l2_mb = l2_mb_env > 0 ? l2_mb_env : (K < 2048 ? 16 : 32);
+        int64_t gm = ((int64_t)l2_mb << 20) / per_block;
         p.group_m = (int)(gm < 4 ? 4 : gm > 32 ? 32 : gm);
     }
     if (ln_stats || stats_out) {          // separate instantiation: the plain kernel carries none of the LayerNorm-fold code
