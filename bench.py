@@ -55,14 +55,34 @@ def peaks():
 MEASURED_TRAFFIC_SRC = "profiles/ncu_traffic.json"
 
 
+SHIPPED_L2_GROUP_MB = 32          # csrc/gemm2_sm100.cu: A-row panel per tile group for K >= 2048
+
+
 def measured_traffic(key: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this round (None if absent)"""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture of this round.  None if absent or if
+    the capture was taken with a different L2 group size than the shipped build (see traffic_note)."""
     p = os.path.join(ROOT, MEASURED_TRAFFIC_SRC)
     if not os.path.exists(p):
         return None
     with open(p) as f:
         d = json.load(f)
-    return d.get(key, {}).get("dram_bytes")
+    e = d.get(key, {})
+    if "l2_group_mb" in e and e["l2_group_mb"] != SHIPPED_L2_GROUP_MB:
+        return None
+    return e.get("dram_bytes")
+
+
+def traffic_note(key: str):
+    p = os.path.join(ROOT, MEASURED_TRAFFIC_SRC)
+    if not os.path.exists(p):
+        return "no ncu capture committed"
+    with open(p) as f:
+        d = json.load(f)
+    near = {k: (v.get("l2_group_mb"), v.get("dram_bytes")) for k, v in d.items() if k.startswith(key)}
+    if d.get(key, {}).get("l2_group_mb", SHIPPED_L2_GROUP_MB) == SHIPPED_L2_GROUP_MB:
+        return None
+    return (f"not captured at the shipped {SHIPPED_L2_GROUP_MB} MB L2 group; same launch at other group sizes (MB, dram bytes): "
+            + ", ".join(f"{mb}: {b}" for mb, b in sorted(near.values(), key=lambda t: -(t[0] or 0))) + "; algorithmic 4.72 GB")
 
 
 def multi_gpu_parity_check(eng, cfg, rank, world, dev):
@@ -405,6 +425,7 @@ def run_ours(args):
                     # from the round's committed `ncu --set full` capture; the family total is not a per-launch quantity
                     traffic=measured_traffic("gate_up126k_2cta" if eng.llm_cta2 else "gate_up126k") if (world == 1 and args.workload == "c3") else None,
                     traffic_of="gate||up + GeGLU launch of the stream pass, M=126000 (algorithmic 4.72 GB)", traffic_src=MEASURED_TRAFFIC_SRC,
+                    traffic_note=traffic_note("gate_up126k_2cta" if eng.llm_cta2 else "gate_up126k"),
                     launches=n_l, share_of_step=round(tot_ms / ms, 4),
                     by_site={k: dict(tflops=round(v[0] / v[1] / 1e9, 1), ms_per_step=round(v[1] / args.steps, 3), launches=v[2] // args.steps)
                              for k, v in sorted(by_tag.items()) if v[1] > 0})
