@@ -9,7 +9,7 @@ projectors, the 42-layer Dattn stream pass, the text pass, lm_head) with random-
 Vidi1.5-9B architecture.  Default workload c3 = BASELINE config 3 (1-hour video: F=3600, C=120 -> 90 000 image +
 36 000 audio + 32 text tokens = 126 032, "~128k"); the same fixed workload is used at every N (strong scaling):
 frames / chunks / tokens are sharded over ranks, the text stream is replicated, and the only data-path
-collective is the per-layer all-gather of the cross-attention (O, LSE) partials.
+exchange is the per-layer push of the cross-attention (O, LSE) partials into the peers' arenas (no collective call).
 Inputs are ~3.3 GB per step (> 126 MB L2) and every activation buffer is far larger than L2, so no explicit
 L2 flush is needed between steps (stated in config.l2).
 """

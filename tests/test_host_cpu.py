@@ -205,3 +205,38 @@ def test_text_pass_descriptor_layout_matches_the_c_compiler(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert [int(x) for x in out[:3]] == [C.sizeof(VidiTextLayerW), C.sizeof(VidiTextSeg), C.sizeof(VidiTextPass)]
     assert [int(x) for x in out[3:]] == [getattr(VidiTextPass, n).offset for n in fields]
+
+
+def test_xattn_split_plan_properties():
+    """key-split plan of the one-launch cross attention: both segments together fill the SMs once (<= n_sms // kv_heads splits),
+    every segment keeps at least one split and at most one per 512 keys, and the plan is the same on every rank (it is computed from
+    the per-rank share of the GLOBAL key counts)."""
+    from vidi_b200 import ops
+    assert ops.xattn_split_plan([90000, 36000], 8) == [13, 5]                     # C3 on one GPU: 18 splits x 8 KV heads = 144 CTAs
+    assert ops.xattn_split_plan([11250, 4500], 8) == [13, 5]                      # C3 on 8 GPUs (per-rank share)
+    for keys in ([0, 300], [1, 1], [511, 513], [5000], [126000], [100, 70000], [70000, 100], [0], [0, 0]):
+        for hkv in (2, 8):
+            plan = ops.xattn_split_plan(keys, hkv, 148)
+            assert len(plan) == len(keys) and all(p >= 1 for p in plan)
+            assert sum(plan) <= max(len(keys), 148 // hkv)
+            assert all(p <= max(1, (k + 511) // 512) for p, k in zip(plan, keys))
+
+
+def test_exchange_arena_layout_arithmetic():
+    """exchange.py: arena = data fp32 [2 slots][world][cap] | flags uint32 [2 slots][world] | counter | err; one rank block holds up to
+    two streams of (O [rows, dh] | LSE [rows]); the text pass's slot / flag addressing in csrc/textpass.cu uses the same numbers."""
+    from vidi_b200.exchange import PartialExchange, arena_bytes
+    rows, dh = 256 * 16, 256
+    cap = PartialExchange.capacity(rows, dh)
+    assert cap == 2 * rows * (dh + 1)
+    for world in (2, 4, 8):
+        n = arena_bytes(world, cap)
+        assert n == 2 * world * cap * 4 + 2 * world * 4 + 8 and n % 4 == 0
+        flags_off = 2 * world * cap * 4
+        for seq in (1, 2, 3, 42, 43):
+            slot = seq & 1
+            for r in range(world):
+                data = slot * world * cap * 4 + r * cap * 4          # block of rank r in the slot
+                flag = flags_off + (slot * world + r) * 4
+                assert 0 <= data and data + cap * 4 <= flags_off and flags_off <= flag < flags_off + 2 * world * 4
+    assert 8 * arena_bytes(8, cap) < 2 ** 31                          # C3 text rows at 8 ranks: well under 2 GB in total

@@ -8,7 +8,8 @@ layers (gemma.py:183-202 reads only the stream itself), so
   3. the short text stream then runs its layers against that cache with the split-KV
      cross-attention kernel; across GPUs only the (O, LSE) partials are exchanged  (text_pass)
 Frames / chunks / tokens are sharded contiguously over ranks (ShardPlan); the text stream is replicated.
-Nothing here computes on the CPU; torch supplies memory, streams and the NCCL all-gather only.
+Nothing here computes on the CPU; torch supplies memory and streams; the multi-GPU exchange of the partials is peer-memory stores
+(exchange.py / csrc/xchg.cu), with one NCCL all-gather per layer only as the fall-back when the arenas cannot be mapped.
 """
 from __future__ import annotations
 
@@ -446,7 +447,7 @@ class Vidi15Engine:
         S, seg = self.encode_streams(images, mels, plan, image_valid, audio_valid)
         if self.overlap_text and S.shape[0] > 0:
             # The text stream's layer l only needs K||V of layer l: run it on a side stream one step behind the stream
-            # pass, so its ~700 small launches (and, multi-GPU, the per-layer all-gather) hide under the big GEMMs.
+            # pass, so its ~500 small launches (and, multi-GPU, the per-layer exchange) hide under the big GEMMs.
             c = self.cfg.llm
             kv = torch.empty(c.layers, S.shape[0], 2 * c.kv_dim, device=self.device, dtype=BF16)
             main = torch.cuda.current_stream()
