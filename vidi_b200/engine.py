@@ -329,8 +329,8 @@ class Vidi15Engine:
         """ids [Tq] int64 (sentinel already stripped) -> logits fp32 [Tq or k, vocab].
         seg: list of (row0, n_rows, kmask or None, gate, n_total) describing the image / audio row ranges of the
         local K||V cache.  (gemma.py:160-175, 185-192, 206-221, 236-238, 564-569)"""
-        if self.native_text and (self.world == 1 or (self.xchg is not None and self.xchg.fits(len(seg), ids.numel() * self.cfg.llm.heads,
-                                                                                              self.cfg.llm.head_dim))):
+        if self.native_text and (self.world == 1 or not seg or (self.xchg is not None and
+                                                                self.xchg.fits(len(seg), ids.numel() * self.cfg.llm.heads, self.cfg.llm.head_dim))):
             return self._text_pass_native(ids, kv, seg, text_cache, logits_to_keep)
         run = _TextRun(self, ids, kv, seg, text_cache, logits_to_keep)
         for l in range(len(self.W.layers)):
@@ -390,9 +390,10 @@ class Vidi15Engine:
             sg = d.seg[i]
             sg.row0, sg.rows, sg.gate, sg.splits = r0, nr, gate, sp
             sg.kmask = kmask.data_ptr() if (kmask is not None and kmask.numel()) else None
-        d.world, d.rank = self.world, self.rank
+        multi = self.world > 1 and len(seg) > 0           # a text-only query has nothing to exchange: every rank runs it alone
+        d.world, d.rank = (self.world, self.rank) if multi else (1, 0)
         x = self.xchg
-        if self.world > 1:
+        if multi:
             d.seq0, d.cap = x.seq, x.cap
             for r in range(self.world):
                 d.peer_data[r] = x.arenas[r]
@@ -407,7 +408,7 @@ class Vidi15Engine:
         logits = torch.empty(keep, c.vocab, device=self.device, dtype=torch.float32)
         d.workspace, d.workspace_bytes, d.logits = ws.data_ptr(), ws.numel(), logits.data_ptr()
         _lib.check(L.vidi_text_pass(C.byref(d), ops._stream()), "text_pass")
-        if self.world > 1:
+        if multi:
             x.seq += c.layers
         if text_cache is not None:
             text_cache["len"] = d.pos0 + Tq
